@@ -1,0 +1,225 @@
+/*
+ * pyrayt_b200 -- C ABI of the B200-native ray-propagation hot path.
+ *
+ * This is the drop-in boundary underneath PyRayT's Python API.  The reference
+ * (rfrazier716/PyRayT v0.3.1) is pure Python/NumPy and has no FFI of its own;
+ * each entry point below names the reference interface it replaces so a
+ * maintainer can bind it with ctypes:
+ *
+ *   prt_scene_create     <- the live scene RayTracer holds: RayTracer.__init__
+ *                           components + _surface_lut (pyrayt/_pyrayt.py:211-260),
+ *                           TracerSurface matrices/primitives/materials
+ *                           (tinygfx/g3d/world_objects.py:338-423),
+ *                           CSGSurface trees + _aobb (tinygfx/g3d/csg.py:64-116)
+ *   prt_trace            <- RayTracer._st_propagate + _st_interact generation loop
+ *                           (pyrayt/_pyrayt.py:370-452) and everything under it:
+ *                           TracerSurface.intersect / get_world_normals
+ *                           (world_objects.py:360-418), CSGSurface.intersect +
+ *                           array_csg (csg.py:13-160), primitives' intersect/normal
+ *                           (primitives.py:241-741), reflect/refract
+ *                           (operations.py:86-162), materials' trace/index_at
+ *                           (pyrayt/materials.py:47-145) and the per-generation
+ *                           record of _RayTraceDataframe.insert (_pyrayt.py:168-186)
+ *   prt_scan_runs +
+ *   prt_gather_frame     <- the (generation, id) row order produced by
+ *                           DataFrame.append per generation (_pyrayt.py:186,:428-435)
+ *   prt_intersect        <- component.intersect(rays) -> (hits(m,N), surface_ids(m,N))
+ *                           (world_objects.py:360-383, csg.py:118-160)
+ *   prt_generate_source  <- Source.generate_rays (pyrayt/components.py:481-496) for the
+ *                           seeded synthetic benchmark sources
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function
+ * returns 0 on success or a negative prt_status and never throws; the message
+ * of the last failure on the calling thread is prt_last_error().  All d_*
+ * pointers are device pointers owned by the caller (the Python host allocates
+ * them as torch tensors); the library performs no hidden allocation and no
+ * stream synchronisation inside prt_trace / prt_scan_runs / prt_gather_frame /
+ * prt_intersect / prt_generate_source: they enqueue work on `cuda_stream`
+ * (a cudaStream_t passed as void*) and return.
+ *
+ * All arithmetic is IEEE float64 (the reference computes in float64).
+ */
+#ifndef PYRAYT_B200_H
+#define PYRAYT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRT_ABI_VERSION 1
+
+/* rows of the reference RaySet, (13, N) float64 row-major (pyrayt/_pyrayt.py:13-144) */
+#define PRT_RAY_ROWS 13
+/* columns of the results frame (pyrayt/_pyrayt.py:15,:154-165):
+ * generation,intensity,wavelength,index,id,surface,x0,y0,z0,x1,y1,z1,x_tilt,y_tilt,z_tilt */
+#define PRT_FRAME_COLS 15
+/* hit slots one component may produce = 2 x leaves of the component */
+#define PRT_MAX_SLOTS 32
+/* largest scene the kernel stages in shared memory */
+#define PRT_MAX_LEAVES 128
+#define PRT_MAX_NODES 256
+
+typedef enum prt_status {
+  PRT_OK = 0,
+  PRT_ERR_INVALID = -1,   /* bad argument / malformed scene            */
+  PRT_ERR_CUDA = -2,      /* CUDA runtime failure (see prt_last_error) */
+  PRT_ERR_LIMIT = -3,     /* scene exceeds PRT_MAX_*                   */
+  PRT_ERR_UNSUPPORTED = -4
+} prt_status;
+
+/* primitive type codes: tinygfx/g3d/primitives.py Sphere:220 Paraboloid:299 Plane:422 Cube:501 Cylinder:621 */
+typedef enum prt_prim {
+  PRT_SPHERE = 1,     /* param[0]=radius                                             */
+  PRT_PARABOLOID = 2, /* param[0]=focus, [1]=height                                  */
+  PRT_PLANE = 3,      /* param[0]=width(x), [1]=length(y)                            */
+  PRT_CUBE = 4,       /* param = x_lo,x_hi,y_lo,y_hi,z_lo,z_hi (Cube.axis_spans)     */
+  PRT_CYLINDER = 5    /* param[0]=radius, [1]=h_min, [2]=h_max, [3]=capped (0/1)     */
+} prt_prim;
+
+/* postfix node kinds; the CSG values equal tinygfx.g3d.csg.Operation (csg.py:7-10) */
+typedef enum prt_node_kind { PRT_LEAF = 0, PRT_UNION = 1, PRT_INTERSECT = 2, PRT_DIFFERENCE = 3 } prt_node_kind;
+
+/* material kinds: pyrayt/materials.py absorber:47 mirror:58 BasicRefractor:102 SellmeierRefractor:121 */
+typedef enum prt_material {
+  PRT_MAT_ABSORBER = 0,
+  PRT_MAT_MIRROR = 1,
+  PRT_MAT_GLASS_CONST = 2,     /* matp[0] = refractive index                      */
+  PRT_MAT_GLASS_SELLMEIER = 3, /* matp = b1,b2,b3,c1,c2,c3                        */
+  PRT_MAT_UNTRACEABLE = 4      /* no .trace(): a hit raises in the reference (Q9) */
+} prt_material;
+
+/*
+ * Host-side flat scene, SoA.  Components are listed in RayTracer order; each
+ * component is a postfix CSG program over nodes [comp_node_begin[c],
+ * comp_node_begin[c+1]).  A bare TracerSurface component is a single PRT_LEAF.
+ */
+typedef struct prt_scene_desc {
+  int32_t n_components;
+  int32_t n_nodes;
+  int32_t n_leaves;
+  int32_t reserved;
+  const int32_t* comp_node_begin; /* [n_components+1]                                          */
+  const int32_t* node_kind;       /* [n_nodes] prt_node_kind                                   */
+  const int32_t* node_leaf;       /* [n_nodes] leaf index for PRT_LEAF nodes, else -1          */
+  const double* node_aabb;        /* [n_nodes*6] CSGSurface._aobb.axis_spans (x_lo,x_hi,y_lo,..)*/
+  const int32_t* leaf_type;       /* [n_leaves] prt_prim                                       */
+  const double* leaf_obj;         /* [n_leaves*16] row-major 4x4 world->object matrix          */
+  const double* leaf_param;       /* [n_leaves*6]                                              */
+  const double* leaf_nscale;      /* [n_leaves] Intersectable._normal_scale (+1/-1)            */
+  const int64_t* leaf_sid;        /* [n_leaves] CountedObject id written to the `surface` col  */
+  const int32_t* leaf_mat;        /* [n_leaves] prt_material                                   */
+  const double* leaf_matp;        /* [n_leaves*6]                                              */
+} prt_scene_desc;
+
+typedef struct prt_scene prt_scene; /* opaque, owns a small device copy of the flattened scene */
+
+typedef enum prt_record_mode {
+  PRT_RECORD_ALL = 0,     /* every segment (the reference frame)               */
+  PRT_RECORD_SURFACE = 1, /* only rows whose surface id == params.detector_sid */
+  PRT_RECORD_NONE = 2     /* counters only                                     */
+} prt_record_mode;
+
+typedef struct prt_params {
+  int32_t generation_limit; /* RayTracer generation_limit (pyrayt/_pyrayt.py:212,:444)  */
+  int32_t record_mode;      /* prt_record_mode                                          */
+  int32_t flags;            /* reserved, 0                                              */
+  int32_t reserved;
+  double ray_offset;        /* RayTracer.ray_offset_value = 1e-6 (pyrayt/_pyrayt.py:190)*/
+  int64_t detector_sid;     /* for PRT_RECORD_SURFACE                                   */
+} prt_params;
+
+/* device-resident counters, zeroed by the caller before prt_trace */
+typedef struct prt_counters {
+  uint64_t rays;               /* rays handed in                                                     */
+  uint64_t generations;        /* sum over rays of generations entered; x n_leaves = ray-surface tests */
+  uint64_t segments;           /* rows the trace produced (whether or not capacity allowed the write)  */
+  uint64_t rows_reserved;      /* append cursor: staging rows reserved                                 */
+  uint64_t rows_dropped;       /* rows not written because staging capacity was exhausted              */
+  uint64_t tie_rays;           /* rays whose CSG merge compared equal finite keys of different leaves  */
+  uint64_t untraceable_hits;   /* nearest hit landed on a PRT_MAT_UNTRACEABLE surface                  */
+  uint64_t bad_w;              /* rays whose homogeneous w rows are not (1, 0)                         */
+  uint64_t nan_rays;           /* rays terminated because their direction became NaN                   */
+  uint64_t limit_rays;         /* rays stopped by generation_limit                                     */
+  uint64_t reserved[6];
+} prt_counters;
+
+/*
+ * Caller-owned record workspace.  The trace kernel processes rays in tiles of
+ * prt_tile_rays() consecutive rays; at every generation a tile appends its
+ * surviving rays' rows (in ray order) as one contiguous run to the
+ * column-major staging buffer and notes (start, count) in the run table.
+ */
+typedef struct prt_records {
+  double* d_stage;      /* [PRT_FRAME_COLS * capacity] staging, column c row r at d_stage[c*capacity + r] */
+  int64_t capacity;     /* rows                                                                           */
+  int64_t* d_run_start; /* [generation_limit * n_tiles], index g*n_tiles + tile                           */
+  int32_t* d_run_count; /* [generation_limit * n_tiles]                                                   */
+  int64_t* d_run_base;  /* [generation_limit * n_tiles] filled by prt_scan_runs: final frame row of run   */
+  int64_t n_tiles;      /* >= ceil(n_rays / prt_tile_rays())                                              */
+} prt_records;
+
+int prt_abi_version(void);
+const char* prt_last_error(void);
+int prt_tile_rays(void);
+
+int prt_scene_create(const prt_scene_desc* host_scene, int device, prt_scene** out);
+void prt_scene_destroy(prt_scene* scene);
+int prt_scene_n_leaves(const prt_scene* scene);
+
+/*
+ * Trace n_rays rays through every generation.  d_rays is the reference RaySet
+ * layout: row k of ray i at d_rays[k*ray_stride + i], rows = x,y,z,w(=1),
+ * dx,dy,dz,w(=0),generation,intensity,wavelength,index,id.
+ * d_run_count must be zeroed by the caller when record_mode != PRT_RECORD_NONE.
+ */
+int prt_trace(prt_scene* scene, const prt_params* params, const double* d_rays, int64_t n_rays,
+              int64_t ray_stride, const prt_records* records, prt_counters* d_counters,
+              void* cuda_stream);
+
+/*
+ * Turn the run table into final frame positions: d_gen_offsets[g] (g = 0 ..
+ * generation_limit) receives the first frame row of generation g and
+ * d_gen_offsets[generation_limit] the total row count.  The caller may rewrite
+ * d_gen_offsets before prt_gather_frame (multi-GPU: shift every generation by the
+ * rows lower ranks contribute to it, from the all-gathered per-rank counts).
+ */
+int prt_scan_runs(const prt_records* records, int32_t generation_limit, int64_t* d_gen_offsets,
+                  void* cuda_stream);
+
+/*
+ * Copy staged rows to the final frame in (generation, id) order.
+ * layout 0: column-major, column c row r at frame[c*frame_stride + r]  (what pandas holds)
+ * layout 1: row-major,    row r column c at frame[r*PRT_FRAME_COLS + c]
+ * `frame` may be any device-accessible pointer, including pinned host memory.
+ */
+int prt_gather_frame(const prt_records* records, int32_t generation_limit, const int64_t* d_gen_offsets,
+                     double* frame, int64_t frame_stride, int32_t layout, void* cuda_stream);
+
+/*
+ * component.intersect(rays): d_rays is (2,4,N) like the reference (row k of ray i
+ * at d_rays[k*n + i]); writes hits (m,N) ascending with +inf padding and the
+ * surface ids (m,N) (-1 where the reference reports -1 or the slot is +inf).
+ * m = 2 x leaves of the component (returned through *slots_out when non-NULL).
+ */
+int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int64_t n,
+                  double* d_hits, int64_t* d_sids, int32_t* slots_out, void* cuda_stream);
+
+/* seeded synthetic sources of SURVEY.md 8(d); see pyrayt_b200/sources.py for the exact law */
+typedef struct prt_source_desc {
+  int32_t kind;        /* 1 = disk/field/wavelength fan (config 4), 2 = solid-angle cone (config 2),
+                          3 = Lambertian cone (config 5)                                              */
+  int32_t reserved;
+  uint64_t seed;
+  double origin[3];
+  double p[16];        /* kind-specific parameters                                                    */
+} prt_source_desc;
+
+int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_rays, int64_t ray_stride,
+                        int64_t first_index, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRAYT_B200_H */

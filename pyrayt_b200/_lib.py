@@ -1,0 +1,118 @@
+"""ctypes binding of ``libpyrayt_b200.so`` (the C ABI in include/pyrayt_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or will not
+load, every entry point raises.  Build it with ``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C pyrayt_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpyrayt_b200.so")
+
+ABI_VERSION = 1
+FRAME_COLS = 15
+RAY_ROWS = 13
+RECORD_ALL, RECORD_SURFACE, RECORD_NONE = 0, 1, 2
+
+FRAME_COLUMNS = (
+    "generation", "intensity", "wavelength", "index", "id", "surface",
+    "x0", "y0", "z0", "x1", "y1", "z1", "x_tilt", "y_tilt", "z_tilt",
+)  # pyrayt/_pyrayt.py:15,:154-165
+
+COUNTER_FIELDS = (
+    "rays", "generations", "segments", "rows_reserved", "rows_dropped", "tie_rays",
+    "untraceable_hits", "bad_w", "nan_rays", "limit_rays",
+)
+COUNTER_WORDS = 16
+
+# every symbol include/pyrayt_b200.h declares
+EXPORTS = (
+    "prt_abi_version", "prt_last_error", "prt_tile_rays", "prt_scene_create", "prt_scene_destroy",
+    "prt_scene_n_leaves", "prt_trace", "prt_scan_runs", "prt_gather_frame", "prt_intersect",
+    "prt_generate_source",
+)
+
+
+class PrtError(RuntimeError):
+    pass
+
+
+class PrtParams(ctypes.Structure):
+    _fields_ = [
+        ("generation_limit", ctypes.c_int32),
+        ("record_mode", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("ray_offset", ctypes.c_double),
+        ("detector_sid", ctypes.c_int64),
+    ]
+
+
+class PrtRecords(ctypes.Structure):
+    _fields_ = [
+        ("d_stage", ctypes.c_void_p),
+        ("capacity", ctypes.c_int64),
+        ("d_run_start", ctypes.c_void_p),
+        ("d_run_count", ctypes.c_void_p),
+        ("d_run_base", ctypes.c_void_p),
+        ("n_tiles", ctypes.c_int64),
+    ]
+
+
+class PrtSourceDesc(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("seed", ctypes.c_uint64),
+        ("origin", ctypes.c_double * 3),
+        ("p", ctypes.c_double * 16),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library or fail loudly (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PrtError(
+            f"{LIB_PATH} is missing: the B200 trace kernels are not built and pyrayt_b200 has no CPU "
+            "fallback.  Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc)."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.prt_abi_version.restype = ctypes.c_int
+    lib.prt_last_error.restype = ctypes.c_char_p
+    lib.prt_tile_rays.restype = ctypes.c_int
+    lib.prt_scene_create.restype = ctypes.c_int
+    lib.prt_scene_create.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.prt_scene_destroy.restype = None
+    lib.prt_scene_destroy.argtypes = [vp]
+    lib.prt_scene_n_leaves.restype = ctypes.c_int
+    lib.prt_scene_n_leaves.argtypes = [vp]
+    lib.prt_trace.restype = ctypes.c_int
+    lib.prt_trace.argtypes = [vp, ctypes.POINTER(PrtParams), vp, i64, i64, ctypes.POINTER(PrtRecords), vp, vp]
+    lib.prt_scan_runs.restype = ctypes.c_int
+    lib.prt_scan_runs.argtypes = [ctypes.POINTER(PrtRecords), i32, vp, vp]
+    lib.prt_gather_frame.restype = ctypes.c_int
+    lib.prt_gather_frame.argtypes = [ctypes.POINTER(PrtRecords), i32, vp, vp, i64, i32, vp]
+    lib.prt_intersect.restype = ctypes.c_int
+    lib.prt_intersect.argtypes = [vp, i32, vp, i64, vp, vp, ctypes.POINTER(i32), vp]
+    lib.prt_generate_source.restype = ctypes.c_int
+    lib.prt_generate_source.argtypes = [ctypes.POINTER(PrtSourceDesc), vp, i64, i64, i64, vp]
+    if lib.prt_abi_version() != ABI_VERSION:
+        raise PrtError(f"ABI mismatch: library {lib.prt_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().prt_last_error()
+        raise PrtError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

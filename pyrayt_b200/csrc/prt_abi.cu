@@ -1,0 +1,193 @@
+// C-ABI layer of pyrayt_b200 (include/pyrayt_b200.h): argument validation, scene
+// encoding (postfix CSG -> preorder program with bounding-box skip targets) and
+// kernel launches.  No torch types; device buffers belong to the caller.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pyrayt_b200.h"
+#include "prt_scene.h"
+#include "prt_encode.h"
+
+
+extern "C" {
+cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, cudaStream_t st);
+cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
+                            long long* gen_offsets, cudaStream_t st);
+cudaError_t prt_launch_gather(const double* stage, long long capacity, const long long* run_start,
+                              const int* run_count, const long long* run_base, long long n_tiles,
+                              const long long* gen_offsets, int generation_limit, double* frame,
+                              long long frame_stride, int layout, cudaStream_t st);
+cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int component, const double* rays,
+                                 long long n, double* hits, long long* sids, int slots, cudaStream_t st);
+cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
+                              long long first, cudaStream_t st);
+}
+
+struct prt_scene {
+  int device = 0;
+  unsigned char* d_blob = nullptr;
+  int blob_bytes = 0;
+  int n_leaves = 0;
+  int n_components = 0;
+  std::vector<int> comp_slots;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return PRT_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+int prt_abi_version(void) { return PRT_ABI_VERSION; }
+const char* prt_last_error(void) { return g_err.c_str(); }
+int prt_tile_rays(void) { return prt::kTileRays; }
+
+int prt_scene_create(const prt_scene_desc* d, int device, prt_scene** out) {
+  if (!d || !out) return fail(PRT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  std::vector<unsigned char> blob;
+  std::vector<int> comp_slots;
+  {
+    std::string err;
+    const int rc = prt::encode_scene(d, blob, comp_slots, err);
+    if (rc != PRT_OK) return fail(rc, err);
+  }
+  const int off = (int)blob.size();
+
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  prt_scene* sc = new prt_scene();
+  sc->device = device;
+  sc->blob_bytes = off;
+  sc->n_leaves = d->n_leaves;
+  sc->n_components = d->n_components;
+  sc->comp_slots = comp_slots;
+  e = cudaMalloc(&sc->d_blob, (size_t)off);
+  if (e != cudaSuccess) {
+    delete sc;
+    return cuda_fail(e, "cudaMalloc(scene)");
+  }
+  e = cudaMemcpy(sc->d_blob, blob.data(), (size_t)off, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(sc->d_blob);
+    delete sc;
+    return cuda_fail(e, "cudaMemcpy(scene)");
+  }
+  *out = sc;
+  return PRT_OK;
+}
+
+void prt_scene_destroy(prt_scene* scene) {
+  if (!scene) return;
+  if (scene->d_blob) cudaFree(scene->d_blob);
+  delete scene;
+}
+
+int prt_scene_n_leaves(const prt_scene* scene) { return scene ? scene->n_leaves : 0; }
+
+int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64_t n_rays, int64_t ray_stride,
+              const prt_records* rec, prt_counters* d_counters, void* cuda_stream) {
+  if (!scene || !p || !d_counters) return fail(PRT_ERR_INVALID, "null argument");
+  if (n_rays < 0 || (n_rays > 0 && !d_rays)) return fail(PRT_ERR_INVALID, "bad ray buffer");
+  if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
+  if (p->generation_limit < 1) return fail(PRT_ERR_INVALID, "generation_limit must be >= 1");
+  if (p->record_mode < PRT_RECORD_ALL || p->record_mode > PRT_RECORD_NONE)
+    return fail(PRT_ERR_INVALID, "bad record_mode");
+  const int64_t tiles = (n_rays + prt::kTileRays - 1) / prt::kTileRays;
+  if (tiles > 0x7fffffffLL) return fail(PRT_ERR_LIMIT, "too many rays for one launch");
+  const bool record = p->record_mode != PRT_RECORD_NONE;
+  prt::TraceArgs a;
+  std::memset(&a, 0, sizeof a);
+  if (record) {
+    if (!rec || !rec->d_stage || !rec->d_run_start || !rec->d_run_count)
+      return fail(PRT_ERR_INVALID, "record workspace missing");
+    if (rec->n_tiles < tiles) return fail(PRT_ERR_INVALID, "records.n_tiles too small");
+    if (rec->capacity < 0) return fail(PRT_ERR_INVALID, "negative capacity");
+    a.stage = rec->d_stage;
+    a.capacity = rec->capacity;
+    a.run_start = reinterpret_cast<long long*>(rec->d_run_start);
+    a.run_count = rec->d_run_count;
+    a.n_tiles = rec->n_tiles;
+  }
+  a.blob = scene->d_blob;
+  a.blob_bytes = scene->blob_bytes;
+  a.generation_limit = p->generation_limit;
+  a.record_mode = p->record_mode;
+  a.ray_offset = p->ray_offset;
+  a.detector_sid = (double)p->detector_sid;
+  a.rays = d_rays;
+  a.n_rays = n_rays;
+  a.stride = ray_stride;
+  a.ctr = d_counters;
+  cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "trace kernel launch");
+  return PRT_OK;
+}
+
+int prt_scan_runs(const prt_records* rec, int32_t generation_limit, int64_t* d_gen_offsets, void* cuda_stream) {
+  if (!rec || !rec->d_run_count || !rec->d_run_base || !d_gen_offsets)
+    return fail(PRT_ERR_INVALID, "null argument");
+  if (generation_limit < 1) return fail(PRT_ERR_INVALID, "generation_limit must be >= 1");
+  cudaError_t e = prt_launch_scan(rec->d_run_count, reinterpret_cast<long long*>(rec->d_run_base), rec->n_tiles,
+                                  generation_limit, reinterpret_cast<long long*>(d_gen_offsets),
+                                  (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "scan kernel launch");
+  return PRT_OK;
+}
+
+int prt_gather_frame(const prt_records* rec, int32_t generation_limit, const int64_t* d_gen_offsets, double* frame,
+                     int64_t frame_stride, int32_t layout, void* cuda_stream) {
+  if (!rec || !rec->d_stage || !rec->d_run_start || !rec->d_run_count || !rec->d_run_base || !d_gen_offsets)
+    return fail(PRT_ERR_INVALID, "null argument");
+  if (!frame) return fail(PRT_ERR_INVALID, "null frame");
+  if (layout != 0 && layout != 1) return fail(PRT_ERR_INVALID, "bad layout");
+  if (rec->n_tiles > 0x7fffffffLL) return fail(PRT_ERR_LIMIT, "too many tiles");
+  cudaError_t e = prt_launch_gather(rec->d_stage, rec->capacity, reinterpret_cast<long long*>(rec->d_run_start),
+                                    rec->d_run_count, reinterpret_cast<long long*>(rec->d_run_base), rec->n_tiles,
+                                    reinterpret_cast<const long long*>(d_gen_offsets), generation_limit, frame,
+                                    frame_stride, layout, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "gather kernel launch");
+  return PRT_OK;
+}
+
+int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int64_t n, double* d_hits,
+                  int64_t* d_sids, int32_t* slots_out, void* cuda_stream) {
+  if (!scene) return fail(PRT_ERR_INVALID, "null scene");
+  if (component < 0 || component >= scene->n_components) return fail(PRT_ERR_INVALID, "component out of range");
+  const int slots = scene->comp_slots[component];
+  if (slots_out) *slots_out = slots;
+  if (n == 0) return PRT_OK;
+  if (!d_rays || !d_hits || !d_sids) return fail(PRT_ERR_INVALID, "null buffer");
+  cudaError_t e = prt_launch_intersect(scene->d_blob, scene->blob_bytes, component, d_rays, n, d_hits,
+                                       reinterpret_cast<long long*>(d_sids), slots, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "intersect kernel launch");
+  return PRT_OK;
+}
+
+int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_rays, int64_t ray_stride,
+                        int64_t first_index, void* cuda_stream) {
+  if (!src || (!d_rays && n_rays > 0)) return fail(PRT_ERR_INVALID, "null argument");
+  if (src->kind < 1 || src->kind > 3) return fail(PRT_ERR_INVALID, "unknown source kind");
+  if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
+  cudaError_t e = prt_launch_source(src, d_rays, n_rays, ray_stride, first_index, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "source kernel launch");
+  return PRT_OK;
+}
+
+}  // extern "C"

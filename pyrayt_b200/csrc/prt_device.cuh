@@ -1,0 +1,574 @@
+// Per-ray device functions of the trace kernels (sm_100a).
+//
+// Everything here is PRT_HD (__host__ __device__) so that tests/emul can run the very
+// same per-ray code on the host for debugging; the product library only ever calls
+// these from kernels.  Arithmetic is IEEE float64 without FMA contraction (-fmad=false)
+// in the order of the reference's NumPy expressions.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/pyrayt_b200.h"
+#include "prt_scene.h"
+
+#if defined(__CUDACC__)
+#define PRT_HD __host__ __device__ __forceinline__
+#else
+#define PRT_HD inline
+#endif
+
+namespace prt {
+
+#define PRT_INF (__builtin_huge_val())
+
+// np.isclose(x, 0): |x| <= 1e-8  (NaN / inf -> false)
+PRT_HD bool isz(double x) { return fabs(x) <= 1e-8; }
+// np.isclose(p, v): |p - v| <= 1e-8 + 1e-5 |v|
+PRT_HD bool iscl(double p, double v) {
+  if (isinf(p) || isinf(v)) return p == v;
+  return fabs(p - v) <= (1e-8 + 1e-5 * fabs(v));
+}
+PRT_HD void sort2(double& a, double& b) {
+  if (b < a) {
+    double t = a;
+    a = b;
+    b = t;
+  }
+}
+
+struct SceneView {
+  const BlobHeader* h;
+  const int* comp;
+  const Op* ops;
+  const double* aabb;
+  const Leaf* leaves;
+};
+
+PRT_HD SceneView make_view(const unsigned char* blob) {
+  SceneView s;
+  s.h = reinterpret_cast<const BlobHeader*>(blob);
+  s.comp = reinterpret_cast<const int*>(blob + s.h->off_comp);
+  s.ops = reinterpret_cast<const Op*>(blob + s.h->off_ops);
+  s.aabb = reinterpret_cast<const double*>(blob + s.h->off_aabb);
+  s.leaves = reinterpret_cast<const Leaf*>(blob + s.h->off_leaves);
+  return s;
+}
+
+// ---------------------------------------------------------------- primitives (object space)
+
+// the z-slab clip shared by Cylinder (primitives.py:680-712) and Paraboloid (:369-399)
+PRT_HD void clip_z(double s0, double s1, double zlo, double zhi, double oz, double dz,
+                                       double b0_num, double& t0, double& t1) {
+  const bool par = isz(dz);
+  const double den = dz + (par ? 1.0 : 0.0);
+  double b0 = b0_num / den;
+  double b1 = (zhi - oz) / den;
+  if (par) {
+    b0 = ((oz >= zlo) && (oz <= zhi)) ? -PRT_INF : PRT_INF;
+    b1 = PRT_INF;
+  }
+  sort2(b0, b1);
+  const double lo = fmax(s0, b0);
+  const double hi = fmin(s1, b1);
+  if (lo <= hi) {
+    t0 = lo;
+    t1 = hi;
+  } else {
+    t0 = PRT_INF;
+    t1 = PRT_INF;
+  }
+}
+
+// one slab of Cube.intersect (primitives.py:531-565)
+PRT_HD void cube_axis(double o, double d, double lo, double hi, double& mn, double& mx) {
+  const bool zf = isz(d);
+  const double den = d + (zf ? 1.0 : 0.0);
+  double h0 = -(o - lo) / den;
+  double h1 = -(o - hi) / den;
+  if (zf) {
+    h0 = (o <= hi && o >= lo) ? -PRT_INF : PRT_INF;
+    h1 = PRT_INF;
+  }
+  sort2(h0, h1);
+  mn = h0;
+  mx = h1;
+}
+
+// Cube.intersect (primitives.py:516-581); also every CSG node's world-space AABB (csg.py:126-128)
+PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, double d0, double d1,
+                                          double d2, double& t0, double& t1) {
+  double mn0, mx0, mn1, mx1, mn2, mx2;
+  cube_axis(o0, d0, sp[0], sp[1], mn0, mx0);
+  cube_axis(o1, d1, sp[2], sp[3], mn1, mx1);
+  cube_axis(o2, d2, sp[4], sp[5], mn2, mx2);
+  const double lo = fmax(fmax(mn0, mn1), mn2);
+  const double hi = fmin(fmin(mx0, mx1), mx2);
+  if (lo < hi) {
+    t0 = lo;
+    t1 = hi;
+  } else {
+    t0 = PRT_INF;
+    t1 = PRT_INF;
+  }
+}
+
+// one bounding axis of Plane.intersect (primitives.py:454-469)
+PRT_HD void plane_axis(double o, double d, double dim, double& mn, double& mx) {
+  const bool zf = isz(d);
+  const double half = dim / 2;
+  const double den = d + (zf ? 1.0 : 0.0);
+  double v0 = -(o - half) / den;
+  double v1 = -(o + half) / den;
+  if (zf) {
+    v0 = (fabs(o) <= half) ? -PRT_INF : PRT_INF;
+    v1 = PRT_INF;
+  }
+  sort2(v0, v1);
+  mn = v0;
+  mx = v1;
+}
+
+// TracerSurface.intersect (world_objects.py:360-383): world->object transform, primitive
+// intersect, sort.  Returns the sorted pair (t0 <= t1) or (+inf, +inf).
+PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0, double v1,
+                                          double v2, double& t0, double& t1) {
+  const double o0 = L.m[0] * p0 + L.m[1] * p1 + L.m[2] * p2 + L.m[3];
+  const double o1 = L.m[4] * p0 + L.m[5] * p1 + L.m[6] * p2 + L.m[7];
+  const double o2 = L.m[8] * p0 + L.m[9] * p1 + L.m[10] * p2 + L.m[11];
+  const double d0 = L.m[0] * v0 + L.m[1] * v1 + L.m[2] * v2;
+  const double d1 = L.m[4] * v0 + L.m[5] * v1 + L.m[6] * v2;
+  const double d2 = L.m[8] * v0 + L.m[9] * v1 + L.m[10] * v2;
+  switch (L.type) {
+    case PRT_SPHERE: {  // primitives.py:241-271
+      const double r = L.prm[0];
+      const double a = d0 * d0 + d1 * d1 + d2 * d2;
+      const double b = 2 * (d0 * o0 + d1 * o1 + d2 * o2);
+      const double c = (o0 * o0 + o1 * o1 + o2 * o2) - r * r;
+      const double disc = b * b - 4 * a * c;
+      const double root = sqrt(fmax(0.0, disc));
+      const double den = 2 * a;
+      t0 = (-b + root) / den;
+      t1 = (-b - root) / den;
+      if (!(disc >= 0)) {
+        t0 = PRT_INF;
+        t1 = PRT_INF;
+      }
+      sort2(t0, t1);
+    } break;
+    case PRT_CYLINDER: {  // primitives.py:650-712 + operations.py:28-63
+      const double r = L.prm[0];
+      const double a = d0 * d0 + d1 * d1;
+      const double b = 2 * (d0 * o0 + d1 * o1);
+      const double c = (o0 * o0 + o1 * o1) - r * r;
+      const double disc = b * b - 4 * a * c;
+      const bool lin = isz(a);
+      const double root = sqrt(fmax(0.0, disc));
+      const double den = 2 * a + (lin ? 1.0 : 0.0);
+      double s0 = (-b + root) / den;
+      double s1 = (-b - root) / den;
+      if (!(disc >= 0)) {
+        s0 = PRT_INF;
+        s1 = PRT_INF;
+      }
+      if (lin) {
+        const double l = -c / (b + (b == 0 ? 1.0 : 0.0));
+        s0 = l;
+        s1 = l;
+        if (isz(b)) {
+          s0 = (c <= 0) ? -PRT_INF : PRT_INF;
+          s1 = PRT_INF;
+        }
+      }
+      sort2(s0, s1);
+      clip_z(s0, s1, L.prm[1], L.prm[2], o2, d2, L.prm[1] - o2, t0, t1);
+    } break;
+    case PRT_PARABOLOID: {  // primitives.py:320-399
+      const double f = L.prm[0];
+      const double a = d0 * d0 + d1 * d1;
+      const double b = 2 * (o0 * d0 + o1 * d1) - 4 * f * d2;
+      const double c = (o0 * o0 + o1 * o1) - 4 * f * o2;
+      const double disc = b * b - 4 * a * c;
+      const bool lin = isz(a);
+      const double root = sqrt(fmax(0.0, disc));
+      const double den = 2 * a + (lin ? 1.0 : 0.0);
+      double s0 = (-b + root) / den;
+      double s1 = (-b - root) / den;
+      if (!(disc >= 0)) {
+        s0 = PRT_INF;
+        s1 = PRT_INF;
+      }
+      if (lin) {
+        s0 = -c / (b + (isz(b) ? 1.0 : 0.0));
+        s1 = (d2 >= 0) ? PRT_INF : -PRT_INF;
+      }
+      sort2(s0, s1);
+      clip_z(s0, s1, 0.0, L.prm[1], o2, d2, -o2, t0, t1);
+    } break;
+    case PRT_PLANE: {  // primitives.py:436-492
+      double xmn, xmx, ymn, ymx;
+      plane_axis(o0, d0, L.prm[0], xmn, xmx);
+      plane_axis(o1, d1, L.prm[1], ymn, ymx);
+      const double lo = fmax(xmn, ymn);
+      const double hi = fmin(xmx, ymx);
+      const bool skew = isz(d2);
+      double t = -o2 / (d2 + (skew ? 1.0 : 0.0));
+      if (skew) t = PRT_INF;
+      if (!(t >= lo && t <= hi)) t = PRT_INF;
+      t0 = t;
+      t1 = t;
+    } break;
+    case PRT_CUBE:  // primitives.py:516-581
+      cube_hits(L.prm, o0, o1, o2, d0, d1, d2, t0, t1);
+      break;
+    default:
+      t0 = PRT_INF;
+      t1 = PRT_INF;
+  }
+}
+
+// TracerSurface.get_world_normals (world_objects.py:401-418) with the primitives' normal()
+// (Sphere :273-296, Paraboloid :401-419, Plane :494-498, Cube :583-602, Cylinder :714-741)
+PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double& n0,
+                                             double& n1, double& n2) {
+  const double q0 = L.m[0] * p0 + L.m[1] * p1 + L.m[2] * p2 + L.m[3];
+  const double q1 = L.m[4] * p0 + L.m[5] * p1 + L.m[6] * p2 + L.m[7];
+  const double q2 = L.m[8] * p0 + L.m[9] * p1 + L.m[10] * p2 + L.m[11];
+  double a0, a1, a2;
+  bool unit = false;  // object normal already unit length: the reference still divides by its norm (== 1)
+  switch (L.type) {
+    case PRT_SPHERE:
+      a0 = q0;
+      a1 = q1;
+      a2 = q2;
+      break;
+    case PRT_PARABOLOID:
+      if (iscl(q2, L.prm[1])) {
+        a0 = 0;
+        a1 = 0;
+        a2 = 1;
+        unit = true;
+      } else {
+        a0 = q0;
+        a1 = q1;
+        a2 = -2 * L.prm[0];
+      }
+      break;
+    case PRT_PLANE:
+      a0 = 0;
+      a1 = 0;
+      a2 = 1;
+      unit = true;
+      break;
+    case PRT_CUBE:
+      a0 = iscl(q0, L.prm[1]) ? 1.0 : (iscl(q0, L.prm[0]) ? -1.0 : 0.0);
+      a1 = iscl(q1, L.prm[3]) ? 1.0 : (iscl(q1, L.prm[2]) ? -1.0 : 0.0);
+      a2 = iscl(q2, L.prm[5]) ? 1.0 : (iscl(q2, L.prm[4]) ? -1.0 : 0.0);
+      break;
+    default:  // PRT_CYLINDER
+      a0 = q0;
+      a1 = q1;
+      a2 = 0;
+      if (L.prm[3] != 0.0) {
+        if (iscl(q2, L.prm[1])) {
+          a0 = 0;
+          a1 = 0;
+          a2 = -1;
+          unit = true;
+        }
+        if (iscl(q2, L.prm[2])) {
+          a0 = 0;
+          a1 = 0;
+          a2 = 1;
+          unit = true;
+        }
+      }
+      break;
+  }
+  if (!unit) {
+    const double nrm = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    a0 /= nrm;
+    a1 /= nrm;
+    a2 /= nrm;
+  }
+  // M_obj^T n_obj, w dropped, normalise, flip (world_objects.py:411-418)
+  double w0 = L.m[0] * a0 + L.m[4] * a1 + L.m[8] * a2;
+  double w1 = L.m[1] * a0 + L.m[5] * a1 + L.m[9] * a2;
+  double w2 = L.m[2] * a0 + L.m[6] * a1 + L.m[10] * a2;
+  const double wn = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+  n0 = (w0 / wn) * L.nscale;
+  n1 = (w1 / wn) * L.nscale;
+  n2 = (w2 / wn) * L.nscale;
+}
+
+// ---------------------------------------------------------------- CSG hit lists
+//
+// The reference keeps fixed-length lists padded with +inf (csg.py:152-160).  Entries at
+// +inf always sort behind every other entry and only influence other +inf entries
+// (array_csg's counts are a forward cumsum and the roll() wrap-around reads the last
+// count, which always equals the start value because enter/exit entries pair up), so a
+// list is represented by its prefix of entries < +inf.  Parity is by *index in the child
+// list* exactly as in csg.py:41,:46.
+
+struct HitStack {
+  double t[kMaxDepth * 2][kMaxSlots];
+  unsigned char leaf[kMaxDepth * 2][kMaxSlots];
+  int len[kMaxDepth];
+  unsigned flags;  // bit s: which of the two buffers of level s is live
+};
+
+PRT_HD int buf_of(const HitStack& S, int lvl) { return lvl * 2 + ((S.flags >> lvl) & 1); }
+
+// streaming form of array_csg (csg.py:13-61) + the two argsorts of CSGSurface.intersect (:138-149):
+// L = live buffer of level `lvl`; R = (r_t, r_leaf, nR) supplied by get_r; result replaces L.
+template <class GetRT, class GetRL>
+PRT_HD void merge_lists(HitStack& S, int lvl, int op, int nR, GetRT r_t, GetRL r_leaf,
+                                            bool& tie) {
+  const int src = buf_of(S, lvl);
+  const int dst = src ^ 1;
+  const int nL = S.len[lvl];
+  int i = 0, j = 0, k = 0;
+  int cnt = (op == PRT_DIFFERENCE) ? 1 : 0;
+  const bool is_union = (op == PRT_UNION);
+  const int rflip = (op == PRT_DIFFERENCE) ? 1 : 0;
+  while (i < nL || j < nR) {
+    bool takeL;
+    double tl = 0, tr = 0;
+    if (j >= nR) {
+      takeL = true;
+      tl = S.t[src][i];
+    } else if (i >= nL) {
+      takeL = false;
+      tr = r_t(j);
+    } else {
+      tl = S.t[src][i];
+      tr = r_t(j);
+      takeL = !(tr < tl);  // stable: the left child wins ties (csg.py:36-38, stable argsort)
+      if (tl == tr) tie = true;
+    }
+    const int exitf = takeL ? (i & 1) : ((j & 1) ^ rflip);
+    const int prev = cnt;
+    cnt += exitf ? -1 : 1;
+    const bool keep = is_union ? ((cnt != 0) != (prev != 0)) : (cnt == 2 || prev == 2);
+    if (keep) {
+      S.t[dst][k] = takeL ? tl : tr;
+      S.leaf[dst][k] = takeL ? S.leaf[src][i] : (unsigned char)r_leaf(j);
+      ++k;
+    }
+    if (takeL)
+      ++i;
+    else
+      ++j;
+  }
+  S.len[lvl] = k;
+  S.flags ^= (1u << lvl);
+}
+
+// component.intersect for one ray: runs ops [begin, end); the result is level 0 of S.
+PRT_HD void eval_component(const SceneView& sc, int begin, int end, double p0, double p1,
+                                               double p2, double v0, double v1, double v2, HitStack& S,
+                                               bool& tie) {
+  int sp = 0;
+  int pc = begin;
+  while (pc < end) {
+    const Op op = sc.ops[pc];
+    if (op.kind == OP_ENTER) {
+      double b0, b1;
+      cube_hits(sc.aabb + 6 * op.a, p0, p1, p2, v0, v1, v2, b0, b1);
+      if (!(b0 < PRT_INF)) {  // cube_hits returns finite values or (+inf,+inf): csg.py:126-128
+        S.len[sp++] = 0;
+        pc = op.b;
+        continue;
+      }
+    } else if (op.kind == OP_LEAF) {
+      double t0, t1;
+      leaf_hits(sc.leaves[op.a], p0, p1, p2, v0, v1, v2, t0, t1);
+      const int b = buf_of(S, sp);
+      const int n = (t0 < PRT_INF) ? ((t1 < PRT_INF) ? 2 : 1) : 0;
+      S.t[b][0] = t0;
+      S.t[b][1] = t1;
+      S.leaf[b][0] = (unsigned char)op.a;
+      S.leaf[b][1] = (unsigned char)op.a;
+      S.len[sp++] = n;
+    } else if (op.kind == OP_MERGE_LEAF) {
+      double t0, t1;
+      leaf_hits(sc.leaves[op.b], p0, p1, p2, v0, v1, v2, t0, t1);
+      const int n = (t0 < PRT_INF) ? ((t1 < PRT_INF) ? 2 : 1) : 0;
+      const int lf = op.b;
+      merge_lists(
+          S, sp - 1, op.a, n, [&](int j) { return j ? t1 : t0; }, [&](int) { return lf; }, tie);
+    } else {  // OP_MERGE
+      const int rl = sp - 1;
+      const int rb = buf_of(S, rl);
+      merge_lists(
+          S, sp - 2, op.a, S.len[rl], [&](int j) { return S.t[rb][j]; }, [&](int j) { return (int)S.leaf[rb][j]; },
+          tie);
+      --sp;
+    }
+    ++pc;
+  }
+}
+
+// nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386)
+PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0,
+                                            double v1, double v2, HitStack& S, double& best_t, int& best_leaf,
+                                            bool& tie) {
+  best_t = PRT_INF;
+  best_leaf = -1;
+  const int nc = sc.h->n_components;
+  for (int c = 0; c < nc; ++c) {
+    const int begin = sc.comp[c], end = sc.comp[c + 1];
+    const Op first = sc.ops[begin];
+    if (end - begin == 1 && first.kind == OP_LEAF) {
+      // bare TracerSurface component: no list needed
+      double t0, t1;
+      leaf_hits(sc.leaves[first.a], p0, p1, p2, v0, v1, v2, t0, t1);
+      const double t = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
+      if (t < best_t) {
+        best_t = t;
+        best_leaf = first.a;
+      }
+      continue;
+    }
+    S.flags = 0;
+    eval_component(sc, begin, end, p0, p1, p2, v0, v1, v2, S, tie);
+    const int b = buf_of(S, 0);
+    const int n = S.len[0];
+    for (int k = 0; k < n; ++k) {  // sorted: the first positive entry is the argmin of where(hits>0)
+      const double t = S.t[b][k];
+      if (t > 0) {
+        if (t < best_t) {  // strict: the earlier component wins ties (:384)
+          best_t = t;
+          best_leaf = S.leaf[b][k];
+        }
+        break;
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------- one generation of one ray
+
+struct RayState {
+  double p0, p1, p2, v0, v1, v2, gen, inten, wl, nidx, id;
+};
+
+struct StepOut {
+  bool row;                  // a frame row was produced this generation
+  double sid;                // surface id
+  double e0, e1, e2;         // hit point (x1,y1,z1)
+  double t0n, t1n, t2n;      // unit tilt of the incoming direction
+  double nv0, nv1, nv2;      // direction after the interaction
+  double n_next;             // refractive index after the interaction
+};
+
+struct StepCounters {
+  unsigned gen, seg, tie, untr, nan, lim;
+};
+
+// _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
+// returns true when the ray goes on to generation g+1.
+PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int generation_limit, HitStack& S,
+                       StepOut& o, StepCounters& c) {
+  o.row = false;
+  const double vn = sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
+  if (isz(vn)) return false;  // absorbed / zero direction (_pyrayt.py:415)
+  if (isnan(r.v0) || isnan(r.v1) || isnan(r.v2)) {
+    c.nan++;  // every hit compares false in the reference -> miss
+    return false;
+  }
+  c.gen++;
+  double best_t;
+  int best_leaf;
+  bool tie = false;
+  nearest_hit(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, S, best_t, best_leaf, tie);
+  if (tie) c.tie = 1;
+  if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
+  const Leaf& L = sc.leaves[best_leaf];
+  o.e0 = r.p0 + r.v0 * best_t;  // :404-407
+  o.e1 = r.p1 + r.v1 * best_t;
+  o.e2 = r.p2 + r.v2 * best_t;
+  o.n_next = r.nidx;
+  bool goes_on = true;
+  if (L.mat == PRT_MAT_ABSORBER) {  // materials.py:47-50
+    o.nv0 = 0;
+    o.nv1 = 0;
+    o.nv2 = 0;
+    goes_on = false;  // recorded now, dead next generation (zero direction)
+  } else if (L.mat == PRT_MAT_MIRROR) {  // materials.py:58-62, operations.py:105-107
+    double n0, n1, n2;
+    world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
+    const double dots = r.v0 * n0 + r.v1 * n1 + r.v2 * n2;
+    o.nv0 = r.v0 - 2 * n0 * dots;
+    o.nv1 = r.v1 - 2 * n1 * dots;
+    o.nv2 = r.v2 - 2 * n2 * dots;
+  } else if (L.mat == PRT_MAT_GLASS_CONST || L.mat == PRT_MAT_GLASS_SELLMEIER) {
+    // materials.py:70-75,:112-118,:136-145 ; operations.py:110-162
+    double n0, n1, n2;
+    world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
+    double n_mat;
+    if (L.mat == PRT_MAT_GLASS_CONST) {
+      n_mat = L.matp[0];
+    } else {
+      const double w2 = r.wl * r.wl;
+      n_mat = sqrt(1 + (L.matp[0] * w2) / (w2 - L.matp[3]) + (L.matp[1] * w2) / (w2 - L.matp[4]) +
+                   (L.matp[2] * w2) / (w2 - L.matp[5]));
+    }
+    const double u0 = r.v0 / vn, u1 = r.v1 / vn, u2 = r.v2 / vn;
+    const double cp = u0 * n0 + u1 * n1 + u2 * n2;
+    const bool exiting = cp > 0;  // leaving the glass always enters n = 1 (operations.py:134)
+    const double n2l = exiting ? 1.0 : n_mat;
+    if (exiting) {
+      n0 = -n0;
+      n1 = -n1;
+      n2 = -n2;
+    }
+    const double q = r.nidx / n2l;
+    const double c1 = exiting ? cp : -cp;
+    const double rad = 1 - (q * q) * (1 - c1 * c1);
+    if (rad > 0) {
+      const double k = q * c1 - sqrt(rad);
+      o.nv0 = q * u0 + k * n0;
+      o.nv1 = q * u1 + k * n1;
+      o.nv2 = q * u2 + k * n2;
+      o.n_next = n2l;
+    } else {  // total internal reflection keeps the index
+      const double k = 2 * c1;
+      o.nv0 = u0 + k * n0;
+      o.nv1 = u1 + k * n1;
+      o.nv2 = u2 + k * n2;
+    }
+    const double nn = sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2);
+    o.nv0 /= nn;
+    o.nv1 /= nn;
+    o.nv2 /= nn;
+  } else {
+    c.untr++;  // the reference raises AttributeError here
+    return false;
+  }
+  c.seg++;
+  o.row = true;
+  o.sid = L.sid;
+  o.t0n = r.v0 / vn;  // unit tilt of the incoming direction (:177)
+  o.t1n = r.v1 / vn;
+  o.t2n = r.v2 / vn;
+  if (g + 1 == generation_limit) {
+    c.lim++;
+    return false;
+  }
+  return goes_on;
+}
+
+// generation g -> g+1 (pyrayt/_pyrayt.py:436-449)
+PRT_HD void advance_ray(RayState& r, const StepOut& o, int g, double ray_offset) {
+  r.gen = (double)(g + 1);
+  r.nidx = o.n_next;
+  r.v0 = o.nv0;
+  r.v1 = o.nv1;
+  r.v2 = o.nv2;
+  r.p0 = o.e0 + ray_offset * o.nv0;
+  r.p1 = o.e1 + ray_offset * o.nv1;
+  r.p2 = o.e2 + ray_offset * o.nv2;
+}
+
+}  // namespace prt

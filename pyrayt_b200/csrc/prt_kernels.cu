@@ -1,0 +1,431 @@
+// pyrayt_b200 trace kernels for sm_100a (B200).
+//
+// K1 trace_kernel      one thread = one ray, every generation in a persistent loop
+//                      (replaces RayTracer._st_propagate/_st_interact and everything under
+//                      them: pyrayt/_pyrayt.py:370-452).
+// K2 scan_runs_kernel / gen_offsets_kernel / gather_kernel
+//                      put the staged rows in the reference's (generation, id) order
+//                      (pyrayt/_pyrayt.py:186,:428-435).
+// K3 source kernels    seeded synthetic sources.
+// intersect_kernel     component.intersect(rays) (world_objects.py:360-383, csg.py:118-160).
+//
+// Arithmetic is IEEE float64 with no FMA contraction (the file is compiled with
+// -fmad=false): NumPy never fuses, and the order of operations below follows the
+// reference expressions so that results agree to rounding.  No tensor cores: the
+// work is per-ray scalar math, not a contraction.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/pyrayt_b200.h"
+#include "prt_scene.h"
+#include "prt_device.cuh"
+
+namespace prt {
+
+// ---------------------------------------------------------------- K1: the trace kernel
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool RECORD>
+__global__ void __launch_bounds__(kTileRays) trace_kernel(const TraceArgs a) {
+  extern __shared__ __align__(16) unsigned char s_blob[];
+  __shared__ int s_wcount[kTileRays / 32];
+  __shared__ long long s_base;
+
+  // stage the scene in shared memory once per block
+  {
+    const int words = a.blob_bytes / 8;
+    const double* src = reinterpret_cast<const double*>(a.blob);
+    double* dst = reinterpret_cast<double*>(s_blob);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const SceneView sc = make_view(s_blob);
+
+  const long long tile = blockIdx.x;
+  const long long i = tile * kTileRays + threadIdx.x;
+  const bool valid = i < a.n_rays;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  RayState rs = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+  StepCounters sc_ctr = {0, 0, 0, 0, 0, 0};
+  unsigned c_drop = 0, c_badw = 0;
+  if (valid) {
+    const double* r = a.rays + i;
+    rs.p0 = r[0 * a.stride];
+    rs.p1 = r[1 * a.stride];
+    rs.p2 = r[2 * a.stride];
+    const double pw = r[3 * a.stride];
+    rs.v0 = r[4 * a.stride];
+    rs.v1 = r[5 * a.stride];
+    rs.v2 = r[6 * a.stride];
+    const double vw = r[7 * a.stride];
+    rs.gen = r[8 * a.stride];
+    rs.inten = r[9 * a.stride];
+    rs.wl = r[10 * a.stride];
+    rs.nidx = r[11 * a.stride];
+    rs.id = r[12 * a.stride];
+    if (pw != 1.0 || vw != 0.0) c_badw = 1;
+  }
+  bool alive = valid;
+  HitStack S;
+
+  for (int g = 0; g < a.generation_limit; ++g) {
+    StepOut so;
+    bool write = false;
+    bool next_alive = false;
+    if (alive) {
+      next_alive = trace_step(sc, rs, g, a.generation_limit, S, so, sc_ctr);
+      alive = so.row;
+      write = RECORD && so.row && (a.record_mode == PRT_RECORD_ALL || so.sid == a.detector_sid);
+    }
+
+    if (RECORD) {
+      // block-aggregated append: one reservation per tile and generation, rows in ray order
+      const unsigned m = __ballot_sync(0xffffffffu, write);
+      if (lane == 0) s_wcount[warp] = __popc(m);
+      const int any_alive = __syncthreads_or(next_alive);
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kTileRays / 32; ++w) {
+        const int cw = s_wcount[w];
+        if (w < warp) before += cw;
+        total += cw;
+      }
+      if (threadIdx.x == 0 && total > 0) {
+        const long long base =
+            (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctr->rows_reserved),
+                                 (unsigned long long)total);
+        a.run_start[(long long)g * a.n_tiles + tile] = base;
+        a.run_count[(long long)g * a.n_tiles + tile] = (base + total <= a.capacity) ? total : 0;
+        s_base = base;
+      }
+      __syncthreads();
+      if (write) {
+        const long long run = s_base;
+        if (run + total <= a.capacity) {
+          const long long row = run + before + __popc(m & ((1u << lane) - 1u));
+          double* o = a.stage + row;
+          const long long cs = a.capacity;
+          o[0 * cs] = rs.gen;
+          o[1 * cs] = rs.inten;
+          o[2 * cs] = rs.wl;
+          o[3 * cs] = rs.nidx;
+          o[4 * cs] = rs.id;
+          o[5 * cs] = so.sid;
+          o[6 * cs] = rs.p0;
+          o[7 * cs] = rs.p1;
+          o[8 * cs] = rs.p2;
+          o[9 * cs] = so.e0;
+          o[10 * cs] = so.e1;
+          o[11 * cs] = so.e2;
+          o[12 * cs] = so.t0n;
+          o[13 * cs] = so.t1n;
+          o[14 * cs] = so.t2n;
+        } else {
+          c_drop++;
+        }
+      }
+      if (!any_alive) break;
+    }
+
+    alive = next_alive;
+    if (alive) {
+      advance_ray(rs, so, g, a.ray_offset);
+    } else if (!RECORD) {
+      break;
+    }
+  }
+
+  // counters: warp-reduce, one atomic per warp and counter
+  unsigned long long vals[9] = {valid ? 1ull : 0ull, sc_ctr.gen, sc_ctr.seg, c_drop, sc_ctr.tie ? 1ull : 0ull,
+                                sc_ctr.untr,         c_badw,     sc_ctr.nan, sc_ctr.lim};
+  unsigned long long* dst[9] = {
+      reinterpret_cast<unsigned long long*>(&a.ctr->rays),
+      reinterpret_cast<unsigned long long*>(&a.ctr->generations),
+      reinterpret_cast<unsigned long long*>(&a.ctr->segments),
+      reinterpret_cast<unsigned long long*>(&a.ctr->rows_dropped),
+      reinterpret_cast<unsigned long long*>(&a.ctr->tie_rays),
+      reinterpret_cast<unsigned long long*>(&a.ctr->untraceable_hits),
+      reinterpret_cast<unsigned long long*>(&a.ctr->bad_w),
+      reinterpret_cast<unsigned long long*>(&a.ctr->nan_rays),
+      reinterpret_cast<unsigned long long*>(&a.ctr->limit_rays)};
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const unsigned long long s = warp_sum(vals[q]);
+    if (lane == 0 && s) atomicAdd(dst[q], s);
+  }
+}
+
+// ---------------------------------------------------------------- K2: (generation, id) ordering
+
+// one block per generation: exclusive scan of run_count over tiles -> run_base (relative), total
+__global__ void __launch_bounds__(1024) scan_runs_kernel(const int* run_count, long long* run_base,
+                                                         long long n_tiles, long long* gen_total) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  const int g = blockIdx.x;
+  const int* cnt = run_count + (long long)g * n_tiles;
+  long long* base = run_base + (long long)g * n_tiles;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
+    const long long t = t0 + threadIdx.x;
+    const long long c = (t < n_tiles) ? cnt[t] : 0;
+    long long x = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const long long carry = s_carry;
+    const long long excl = carry + (warp ? s_warp[warp - 1] : 0) + x - c;
+    if (t < n_tiles) base[t] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gen_total[g] = s_carry;
+}
+
+// exclusive scan over generations (tiny): gen_offsets[g] = first row of generation g, [G] = total
+__global__ void gen_offsets_kernel(long long* gen_offsets, int generation_limit) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long acc = 0;
+    for (int g = 0; g < generation_limit; ++g) {
+      const long long c = gen_offsets[g];
+      gen_offsets[g] = acc;
+      acc += c;
+    }
+    gen_offsets[generation_limit] = acc;
+  }
+}
+
+// one block per tile: copy each of the tile's runs to its final frame rows
+template <int LAYOUT>
+__global__ void __launch_bounds__(kTileRays) gather_kernel(const double* stage, long long capacity,
+                                                           const long long* run_start, const int* run_count,
+                                                           const long long* run_base, long long n_tiles,
+                                                           const long long* gen_offsets, int generation_limit,
+                                                           double* frame, long long frame_stride) {
+  const long long tile = blockIdx.x;
+  for (int g = 0; g < generation_limit; ++g) {
+    const long long idx = (long long)g * n_tiles + tile;
+    const int c = run_count[idx];
+    if (c == 0) continue;
+    if ((int)threadIdx.x < c) {
+      const long long src = run_start[idx] + threadIdx.x;
+      const long long dst = gen_offsets[g] + run_base[idx] + threadIdx.x;
+      double v[kFrameCols];
+#pragma unroll
+      for (int k = 0; k < kFrameCols; ++k) v[k] = __ldcs(stage + k * capacity + src);
+      if (LAYOUT == 0) {
+#pragma unroll
+        for (int k = 0; k < kFrameCols; ++k) __stcs(frame + k * frame_stride + dst, v[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kFrameCols; ++k) frame[dst * kFrameCols + k] = v[k];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- component.intersect
+
+__global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned char* blob, int blob_bytes,
+                                                              int component, const double* rays, long long n,
+                                                              double* hits, long long* sids, int slots) {
+  extern __shared__ __align__(16) unsigned char s_blob[];
+  {
+    const int words = blob_bytes / 8;
+    const double* src = reinterpret_cast<const double*>(blob);
+    double* dst = reinterpret_cast<double*>(s_blob);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const SceneView sc = make_view(s_blob);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
+  const double v0 = rays[4 * n + i], v1 = rays[5 * n + i], v2 = rays[6 * n + i];
+  HitStack S;
+  S.flags = 0;
+  bool tie = false;
+  eval_component(sc, sc.comp[component], sc.comp[component + 1], p0, p1, p2, v0, v1, v2, S, tie);
+  const int b = buf_of(S, 0);
+  const int len = S.len[0];
+  for (int k = 0; k < slots; ++k) {
+    hits[k * n + i] = (k < len) ? S.t[b][k] : PRT_INF;
+    sids[k * n + i] = (k < len) ? (long long)sc.leaves[S.leaf[b][k]].sid : -1;
+  }
+}
+
+// ---------------------------------------------------------------- K3: seeded synthetic sources
+//
+// Counter-based uniforms u(i,k) = mix64(seed ^ (i*C1 + k*C2)) >> 11 * 2^-53; only + - * / sqrt
+// follow, so the NumPy restatement (oracle/sources_np.py) is bit-identical.
+
+__device__ __forceinline__ double u01(unsigned long long seed, unsigned long long i, unsigned long long k) {
+  unsigned long long z = seed ^ (i * 0x9E3779B97F4A7C15ull + k * 0xD1B54A32D192ED03ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// rejection-sample a point of the unit disk (radius^2 in (1e-12, 1])
+__device__ __forceinline__ void unit_disk(unsigned long long seed, unsigned long long i, unsigned long long k0,
+                                          double& a, double& b) {
+  a = 0;
+  b = 0;
+  for (unsigned long long k = 0; k < 64; k += 2) {
+    const double x = 2 * u01(seed, i, k0 + k) - 1;
+    const double y = 2 * u01(seed, i, k0 + k + 1) - 1;
+    const double r2 = x * x + y * y;
+    if (r2 <= 1.0 && r2 > 1e-12) {
+      a = x;
+      b = y;
+      return;
+    }
+  }
+}
+
+__global__ void source_kernel(const prt_source_desc src, double* rays, long long n, long long stride,
+                              long long first) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long i = (unsigned long long)(first + j);
+  double px = src.origin[0], py = src.origin[1], pz = src.origin[2];
+  double dx = 1, dy = 0, dz = 0, wl = 0.633, inten = 100.0;
+  if (src.kind == 1) {
+    // collimated field fan: disk of radius p[0] in the plane x = origin.x; field i%3 rotates +x about z
+    // by (cos,sin) = p[2+2f], p[3+2f]; wavelength p[8 + (i/3)%3]; intensity p[11]
+    double a, b;
+    unit_disk(src.seed, i, 0, a, b);
+    py = src.origin[1] + src.p[0] * a;
+    pz = src.origin[2] + src.p[0] * b;
+    const int f = (int)(i % 3ull);
+    dx = src.p[2 + 2 * f];
+    dy = src.p[3 + 2 * f];
+    dz = 0;
+    wl = src.p[8 + (int)((i / 3ull) % 3ull)];
+    inten = src.p[11];
+  } else if (src.kind == 2) {
+    // point source, directions uniform in solid angle inside a cone about +x: p[0] = cos(theta_max)
+    const double ct = 1 - u01(src.seed, i, 0) * (1 - src.p[0]);
+    const double st = sqrt(1 - ct * ct);
+    double a, b;
+    unit_disk(src.seed, i, 1, a, b);
+    const double r = sqrt(a * a + b * b);
+    dx = ct;
+    dy = st * (a / r);
+    dz = st * (b / r);
+    wl = src.p[1];
+    inten = src.p[2];
+  } else if (src.kind == 3) {
+    // point source, Lambertian within a cone about -x: p[0] = sin(theta_max) (Malley's method)
+    double a, b;
+    unit_disk(src.seed, i, 0, a, b);
+    const double u = src.p[0] * a, v = src.p[0] * b;
+    dx = -sqrt(1 - (u * u + v * v));
+    dy = u;
+    dz = v;
+    wl = src.p[1];
+    inten = src.p[2];
+  }
+  double* r = rays + j;
+  r[0 * stride] = px;
+  r[1 * stride] = py;
+  r[2 * stride] = pz;
+  r[3 * stride] = 1.0;
+  r[4 * stride] = dx;
+  r[5 * stride] = dy;
+  r[6 * stride] = dz;
+  r[7 * stride] = 0.0;
+  r[8 * stride] = 0.0;
+  r[9 * stride] = inten;
+  r[10 * stride] = wl;
+  r[11 * stride] = 1.0;
+  r[12 * stride] = (double)i;
+}
+
+}  // namespace prt
+
+// ---------------------------------------------------------------- launchers used by prt_abi.cpp
+
+extern "C" {
+
+cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, cudaStream_t st) {
+  const long long tiles = (a->n_rays + prt::kTileRays - 1) / prt::kTileRays;
+  if (tiles == 0) return cudaSuccess;
+  const size_t smem = (size_t)a->blob_bytes;
+  if (record) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(prt::trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prt::trace_kernel<true><<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(prt::trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prt::trace_kernel<false><<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
+                            long long* gen_offsets, cudaStream_t st) {
+  if (generation_limit <= 0) return cudaSuccess;
+  prt::scan_runs_kernel<<<generation_limit, 1024, 0, st>>>(run_count, run_base, n_tiles, gen_offsets);
+  prt::gen_offsets_kernel<<<1, 32, 0, st>>>(gen_offsets, generation_limit);
+  return cudaGetLastError();
+}
+
+cudaError_t prt_launch_gather(const double* stage, long long capacity, const long long* run_start,
+                              const int* run_count, const long long* run_base, long long n_tiles,
+                              const long long* gen_offsets, int generation_limit, double* frame,
+                              long long frame_stride, int layout, cudaStream_t st) {
+  if (n_tiles == 0) return cudaSuccess;
+  if (layout == 0)
+    prt::gather_kernel<0><<<(unsigned)n_tiles, prt::kTileRays, 0, st>>>(
+        stage, capacity, run_start, run_count, run_base, n_tiles, gen_offsets, generation_limit, frame, frame_stride);
+  else
+    prt::gather_kernel<1><<<(unsigned)n_tiles, prt::kTileRays, 0, st>>>(
+        stage, capacity, run_start, run_count, run_base, n_tiles, gen_offsets, generation_limit, frame, frame_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int component, const double* rays,
+                                 long long n, double* hits, long long* sids, int slots, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + prt::kTileRays - 1) / prt::kTileRays);
+  if (blob_bytes > 48 * 1024)
+    cudaFuncSetAttribute(prt::intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
+  prt::intersect_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, component, rays, n,
+                                                                            hits, sids, slots);
+  return cudaGetLastError();
+}
+
+cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
+                              long long first, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  prt::source_kernel<<<blocks, 256, 0, st>>>(*src, rays, n, stride, first);
+  return cudaGetLastError();
+}
+
+}  // extern "C"

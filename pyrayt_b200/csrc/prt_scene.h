@@ -1,0 +1,71 @@
+// Device-side scene encoding shared by the host ABI layer and the kernels.
+//
+// The caller hands prt_scene_create() postfix CSG programs (include/pyrayt_b200.h);
+// the kernels run a *preorder* program with skip targets so that the bounding-box
+// cull of CSGSurface.intersect (tinygfx/g3d/csg.py:126-133) can skip a whole
+// subtree per ray.  The encoded scene is one contiguous blob that every thread
+// block copies to shared memory once.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/pyrayt_b200.h"
+
+namespace prt {
+
+constexpr int kTileRays = 256;     // rays per tile == threads per block of the trace kernel
+constexpr int kMaxSlots = 32;      // PRT_MAX_SLOTS
+constexpr int kMaxDepth = 6;       // simultaneously live hit lists while evaluating one component
+constexpr int kFrameCols = 15;
+
+enum OpKind : int {
+  OP_LEAF = 0,        // a = leaf              : push the leaf's hit pair
+  OP_ENTER = 1,       // a = aabb, b = skip op : world-space box test; on miss push an empty list and jump to b
+  OP_MERGE = 2,       // a = csg operation     : pop R, pop L, push array_csg(L, R)
+  OP_MERGE_LEAF = 3   // a = csg operation, b = leaf : top := array_csg(top, leaf pair)  (right child is a leaf)
+};
+
+struct Op {
+  int kind, a, b, c;
+};
+
+struct Leaf {
+  double m[12];    // rows 0..2 of the world->object 4x4 (row-major 3x4)
+  double prm[6];   // primitive parameters (see prt_prim)
+  double matp[6];  // material parameters (see prt_material)
+  double nscale;   // Intersectable._normal_scale
+  double sid;      // surface id as it appears in the frame (float64 column)
+  int type;        // prt_prim
+  int mat;         // prt_material
+};
+
+struct BlobHeader {
+  int n_components, n_ops, n_leaves, n_aabb;
+  int off_comp;    // int[n_components+1] : op ranges per component
+  int off_ops;     // Op[n_ops]
+  int off_aabb;    // double[n_aabb*6]
+  int off_leaves;  // Leaf[n_leaves]
+  int total_bytes;
+  int max_slots;   // largest component hit-list length
+  int pad[2];
+};
+
+// arguments of the trace kernel (filled by prt_trace)
+struct TraceArgs {
+  const unsigned char* blob;
+  int blob_bytes;
+  int generation_limit;
+  int record_mode;
+  double ray_offset;
+  double detector_sid;
+  const double* rays;
+  long long n_rays;
+  long long stride;
+  double* stage;
+  long long capacity;
+  long long* run_start;
+  int* run_count;
+  long long n_tiles;
+  prt_counters* ctr;
+};
+
+}  // namespace prt

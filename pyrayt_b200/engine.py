@@ -1,0 +1,196 @@
+"""Device-level driver of the trace kernels: owns the torch buffers, calls the C ABI.
+
+PyTorch is used for device memory, pinned host memory and streams only; every
+kernel that runs here is one of ours (libpyrayt_b200.so).  There is no CPU
+path: constructing an Engine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .scene import FlatScene
+
+_RECORD_MODES = {"all": _lib.RECORD_ALL, "surface": _lib.RECORD_SURFACE, "detector": _lib.RECORD_SURFACE,
+                 "none": _lib.RECORD_NONE}
+
+
+@dataclass
+class TraceResult:
+    frame: Optional[object]      # torch (15, rows) float64: column-major frame (device, or pinned host)
+    rows: int
+    counters: dict
+    gen_counts: Optional[np.ndarray]  # rows per generation (host int64)
+    launches: int                # kernels of ours launched for this trace
+    n_leaves: int
+
+    @property
+    def ray_surface_tests(self) -> int:
+        """sum over generations of live rays x leaf surfaces."""
+        return self.counters["generations"] * self.n_leaves
+
+
+class Engine:
+    """One flattened scene resident on one GPU."""
+
+    def __init__(self, scene: FlatScene, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.PrtError("pyrayt_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self._torch = torch
+        self.lib = _lib.load()
+        self.scene = scene
+        self.device = int(device)
+        self.tile = self.lib.prt_tile_rays()
+        handle = ctypes.c_void_p()
+        desc = scene.as_desc()
+        _lib.check(self.lib.prt_scene_create(ctypes.byref(desc), self.device, ctypes.byref(handle)), "prt_scene_create")
+        self._handle = handle
+        self.n_leaves = scene.n_leaves
+        self.rows_per_ray_hint = 4.0
+        self._ws = {}
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self.lib.prt_scene_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self):
+        return self._torch.device("cuda", self.device)
+
+    def _buf(self, key, numel, dtype):
+        """Grow-only workspace tensors (the ABI never allocates)."""
+        t = self._ws.get(key)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            self._ws[key] = None
+            t = self._torch.empty(int(numel), dtype=dtype, device=self._dev())
+            self._ws[key] = t
+        return t
+
+    def release_workspace(self) -> None:
+        self._ws.clear()
+
+    # ------------------------------------------------------------------ trace
+    def trace(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
+              detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
+              host_frame=None, zero_copy: bool = False) -> TraceResult:
+        """Trace a device RaySet.
+
+        d_rays: torch float64 CUDA tensor (13, N) in the reference RaySet layout.
+        to_host: return the frame in pinned host memory (one D2H copy, or with
+        ``zero_copy`` the gather kernel writes straight into the pinned buffer).
+        """
+        torch = self._torch
+        assert d_rays.is_cuda and d_rays.dtype == torch.float64 and d_rays.dim() == 2
+        assert d_rays.shape[0] == _lib.RAY_ROWS and d_rays.stride(1) == 1
+        n = int(d_rays.shape[1])
+        stride = int(d_rays.stride(0)) if n > 0 else 0
+        G = int(generation_limit)
+        mode = _RECORD_MODES[record]
+        n_tiles = max(1, (n + self.tile - 1) // self.tile)
+        launches = 0
+        with torch.cuda.device(self.device):
+            ctr = self._buf("ctr", _lib.COUNTER_WORDS, torch.int64)
+            params = _lib.PrtParams(G, mode, 0, 0, float(ray_offset), int(detector_sid))
+            if mode == _lib.RECORD_NONE:
+                ctr.zero_()
+                _lib.check(self.lib.prt_trace(self._handle, ctypes.byref(params), d_rays.data_ptr(), n, stride,
+                                              None, ctr.data_ptr(), self._stream()), "prt_trace")
+                launches += 1
+                counters = self._counters(ctr)
+                return TraceResult(None, 0, counters, None, launches, self.n_leaves)
+
+            if G * n_tiles > (1 << 31):
+                raise _lib.PrtError("generation_limit x tiles too large for one call; trace the rays in chunks")
+            cap = int(capacity) if capacity is not None else int(min(n * G, max(n * self.rows_per_ray_hint * 1.05, 4096)))
+            cap = max(cap, 1)
+            while True:
+                stage = self._buf("stage", _lib.FRAME_COLS * cap, torch.float64)
+                run_start = self._buf("run_start", G * n_tiles, torch.int64)
+                run_count = self._buf("run_count", G * n_tiles, torch.int32)
+                run_base = self._buf("run_base", G * n_tiles, torch.int64)
+                gen_off = self._buf("gen_off", G + 1, torch.int64)
+                ctr.zero_()
+                run_count[: G * n_tiles].zero_()
+                rec = _lib.PrtRecords(stage.data_ptr(), cap, run_start.data_ptr(), run_count.data_ptr(),
+                                      run_base.data_ptr(), n_tiles)
+                _lib.check(self.lib.prt_trace(self._handle, ctypes.byref(params), d_rays.data_ptr(), n, stride,
+                                              ctypes.byref(rec), ctr.data_ptr(), self._stream()), "prt_trace")
+                launches += 1
+                _lib.check(self.lib.prt_scan_runs(ctypes.byref(rec), G, gen_off.data_ptr(), self._stream()),
+                           "prt_scan_runs")
+                launches += 2
+                host = torch.cat([ctr, gen_off[: G + 1]]).cpu()  # one small D2H + sync
+                counters = dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in host[: len(_lib.COUNTER_FIELDS)])))
+                goff = host[_lib.COUNTER_WORDS:].numpy()
+                if counters["rows_dropped"] == 0:
+                    break
+                # staging overflowed: the kernel kept counting; retry once with the exact size
+                cap = int(counters["rows_reserved"])
+            rows = int(goff[G])
+            if n > 0:
+                self.rows_per_ray_hint = max(self.rows_per_ray_hint, rows / n)
+            gen_counts = np.diff(goff).astype(np.int64)
+            frame = self._gather(rec, G, gen_off, rows, to_host, host_frame, zero_copy)
+            launches += 1 if rows else 0
+            return TraceResult(frame, rows, counters, gen_counts, launches, self.n_leaves)
+
+    def _gather(self, rec, G, gen_off, rows, to_host, host_frame, zero_copy):
+        torch = self._torch
+        if rows == 0:
+            if to_host:
+                return torch.empty((_lib.FRAME_COLS, 0), dtype=torch.float64)
+            return torch.empty((_lib.FRAME_COLS, 0), dtype=torch.float64, device=self._dev())
+        if to_host and zero_copy:
+            out = host_frame if host_frame is not None else torch.empty(
+                (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
+            assert out.is_pinned() and out.shape[0] == _lib.FRAME_COLS and out.shape[1] >= rows
+            _lib.check(self.lib.prt_gather_frame(ctypes.byref(rec), G, gen_off.data_ptr(), out.data_ptr(),
+                                                 int(out.stride(0)), 0, self._stream()), "prt_gather_frame")
+            torch.cuda.current_stream(self.device).synchronize()
+            return out[:, :rows]
+        frame = torch.empty((_lib.FRAME_COLS, rows), dtype=torch.float64, device=self._dev())
+        _lib.check(self.lib.prt_gather_frame(ctypes.byref(rec), G, gen_off.data_ptr(), frame.data_ptr(), rows, 0,
+                                             self._stream()), "prt_gather_frame")
+        if not to_host:
+            return frame
+        out = host_frame if host_frame is not None else torch.empty(
+            (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
+        out[:, :rows].copy_(frame, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out[:, :rows]
+
+    def _counters(self, ctr) -> dict:
+        host = ctr.cpu()
+        return dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in host[: len(_lib.COUNTER_FIELDS)])))
+
+    # ------------------------------------------------------------------ component.intersect
+    def intersect(self, component: int, d_rays):
+        """component.intersect(rays (2,4,N) device) -> (hits (m,N), surface ids (m,N)) device tensors."""
+        torch = self._torch
+        r = d_rays.reshape(8, -1).contiguous()
+        n = int(r.shape[1])
+        m = self.scene.component_slots(component)
+        hits = torch.empty((m, n), dtype=torch.float64, device=self._dev())
+        sids = torch.empty((m, n), dtype=torch.int64, device=self._dev())
+        slots = ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.prt_intersect(self._handle, component, r.data_ptr(), n, hits.data_ptr(),
+                                              sids.data_ptr(), ctypes.byref(slots), self._stream()), "prt_intersect")
+        assert slots.value == m
+        return hits, sids
