@@ -1,0 +1,352 @@
+"""bench.py -- traced rays/s and ray-surface tests/s of the PyRayT hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload config4] [--rays N] [--impl reference]
+
+One "step" is one full trace of the workload's ray batch: the persistent trace kernel
+(every generation, CSG merging, nearest hit, material interaction, record append) followed by
+the (generation, id) ordering of the records into the 15-column frame.  With N > 1 (launched by
+torchrun, one rank per GPU) every rank traces its own ray-index range of an N x larger source
+("weak" scaling); the only collective is the all-gather of per-generation row counts.
+
+value  = rays/s with the rays already resident in HBM and the frame left in HBM.
+e2e    = the same through the host-buffer API: rays in pinned host memory are copied H2D,
+         traced, ordered, and the whole frame is copied D2H, all inside the timed region.
+roofline / roofline_fp64 / cpu_baseline: see DESIGN.md "Measurement".
+
+--impl reference times the CPU restatement of the reference (oracle/, all host threads) on a
+bounded sample of the same workload; the Python reference itself cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "traced rays/s"
+UNIT = "rays/s"
+CPU_SAMPLE_RAYS = 1 << 18
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config4")
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(workload, n_sample, threads, steps, warmup):
+    """Times the oracle port (CPU restatement of the reference) on the first n_sample rays."""
+    import numpy as np
+
+    from oracle import oracle, sources_np
+
+    scene = workload.scene()
+    rays = sources_np.from_source(workload.source, n_sample)
+    cap = n_sample * min(workload.generation_limit, 40)
+    frame = np.empty((15, cap))
+    times, rows, ctr = [], 0, {}
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        rows, ctr = oracle.trace_timed(scene, rays, workload.generation_limit, 1e-6, threads, frame)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return {"rays_per_s": n_sample / mean, "tests_per_s": ctr["generations"] * scene.n_leaves / mean,
+            "rows": rows, "ms_per_step": mean * 1e3, "counters": ctr}
+
+
+def run_reference(args):
+    """The reference arm: CPU implementation of the path on this box's host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from pyrayt_b200 import workloads
+
+    wl = workloads.WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    n = min(CPU_SAMPLE_RAYS, args.rays or wl.n_rays)
+    r = cpu_reference_run(wl, n, threads, max(1, args.steps), max(0, min(args.warmup, 1)))
+    sample = f"first {n} rays of {wl.name} ({wl.description}), full frame written on the host"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["rays_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.name, "description": wl.description, "generation_limit": wl.generation_limit,
+                   "rays_per_step": n},
+        "ray_surface_tests_per_s": r["tests_per_s"],
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": r["rays_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def fp64_peak_tflops(torch, lib, device):
+    """Measured FP64 FMA rate of this GPU from our own probe kernel (flops = threads*iters*16)."""
+    import ctypes
+
+    scratch = torch.zeros(8, dtype=torch.float64, device=device)
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    blocks, iters = sms * 16, 1 << 15
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.prt_fp64_probe(scratch.data_ptr(), blocks, iters, stream)
+        assert rc == 0
+        e1.record()
+        e1.synchronize()
+        best = max(best, blocks * 256 * iters * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pyrayt_b200
+    from pyrayt_b200 import _lib, roofline, workloads
+    from pyrayt_b200 import dist as pdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+
+    wl = workloads.WORKLOADS[args.workload]
+    n = args.rays or wl.n_rays
+    G = wl.generation_limit
+    scene = wl.scene()
+    engine = pyrayt_b200.Engine(scene, device=local_rank)
+    first = rank * n  # ray-index range of this rank: ids stay global
+    d_rays = wl.source.generate(n, device=local_rank, first_index=first)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ device-resident steps
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    k1_ms, step_ms = [], []
+    res = None
+
+    def device_step(timed):
+        nonlocal res
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        res = engine.trace(d_rays, generation_limit=G, record="all", k1_events=(e0, e1) if timed else None)
+        if world > 1:  # C1: the only data-path collective -- per-generation row counts of every rank
+            pdist.exchange_counts(res.gen_counts, device=device)
+        e2.record()
+        e2.synchronize()
+        if timed:
+            k1_ms.append(e0.elapsed_time(e1))
+            step_ms.append(e0.elapsed_time(e2))
+
+    for _ in range(max(args.warmup, 3)):
+        device_step(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_begin = ev()
+    t_end = ev()
+    t_begin.record()
+    for _ in range(args.steps):
+        device_step(True)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
+    rows = res.rows
+    counters = res.counters
+    launches_per_step = res.launches
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    tests_per_s = sum_over_ranks(res.ray_surface_tests) / (ms_per_step * 1e-3)
+    k1 = sum(k1_ms) / len(k1_ms)
+
+    # ------------------------------------------------------------------ roofline of the trace kernel
+    hbm_peak, peak_src = measured_peaks()
+    abytes = roofline.algorithmic_bytes(n, rows)
+    aflops = roofline.algorithmic_flops(scene, counters)
+    fp64_peak = fp64_peak_tflops(torch, engine.lib, device)
+    roof = {"bound": "hbm", "achieved": abytes / (k1 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": abytes / (k1 * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "kernel": "trace_kernel<true>", "kernel_ms": k1, "algorithmic_bytes_per_launch": abytes,
+            "binding_resource": "fp64 pipe (see roofline_fp64); the HBM fraction is reported per the bench contract"}
+    roof64 = {"bound": "fp64", "achieved": aflops / (k1 * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+              "frac": aflops / (k1 * 1e-3) / 1e12 / fp64_peak,
+              "peak_source": "measured: prt_fp64_probe (DFMA, 2 flops each) on this GPU",
+              "algorithmic_flops_per_launch": aflops,
+              "note": "algorithmic flops are almost all non-FMA (+,-,*,/,sqrt,compare = 1 each)"}
+    traffic_file = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            t = json.load(fh)
+        if t.get("workload") == wl.name and t.get("rays") == n:
+            roof["traffic"] = t.get("dram_bytes_per_launch")
+
+    # ------------------------------------------------------------------ end to end through host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ranks)
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        ns = min(CPU_SAMPLE_RAYS, n)
+        r = cpu_reference_run(wl, ns, threads, 2, 1)
+        cpu = {"value": r["rays_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {ns} rays of {wl.name}, oracle port (C restatement), full frame written",
+               "ray_surface_tests_per_s": r["tests_per_s"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "description": wl.description, "rays_per_gpu": n,
+                       "generation_limit": G, "leaves": scene.n_leaves, "rows_per_ray": rows / n,
+                       "parallelism": f"ray-range x{world}", "l2": "inputs larger than L2 (rays + staging >> 126 MB)"},
+            "ray_surface_tests_per_s": tests_per_s, "segments_per_s": world * rows / (ms_per_step * 1e-3),
+            "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "counters": {k: counters[k] for k in ("rays", "generations", "segments", "tie_rays", "rows_dropped")},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ranks):
+    """Host buffers in, host frame out: H2D of the rays and D2H of the frame inside the timed region."""
+    import psutil
+
+    h_rays = torch.empty(d_rays.shape, dtype=torch.float64, pin_memory=True)
+    h_rays.copy_(d_rays)
+    frame_bytes = rows * 15 * 8
+    avail = psutil.virtual_memory().available
+    if frame_bytes * world * 1.25 > avail:
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": int(h_rays.numel() * 8),
+                "d2h_bytes_per_step": int(frame_bytes), "skipped": "host RAM too small for the pinned frame(s)"}
+    h_frame = torch.empty((15, rows), dtype=torch.float64, pin_memory=True)
+    dev_in = torch.empty_like(d_rays)
+    steps = max(1, min(args.steps, 3))
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step():
+        dev_in.copy_(h_rays, non_blocking=True)
+        r = engine.trace(dev_in, generation_limit=G, record="all", to_host=True, host_frame=h_frame)
+        assert r.rows == rows
+        return r
+
+    step()
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    barrier()
+    ms = max_over_ranks(t0.elapsed_time(t1)) / steps
+    chk = float(h_frame[5, :1024].sum())  # touch the host result
+    return {"value": world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": int(h_rays.numel() * 8), "d2h_bytes_per_step": int(frame_bytes),
+            "host_checksum": chk}
+
+
+if __name__ == "__main__":
+    main()

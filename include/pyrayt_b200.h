@@ -142,7 +142,9 @@ typedef struct prt_counters {
   uint64_t bad_w;              /* rays whose homogeneous w rows are not (1, 0)                         */
   uint64_t nan_rays;           /* rays terminated because their direction became NaN                   */
   uint64_t limit_rays;         /* rays stopped by generation_limit                                     */
-  uint64_t reserved[6];
+  uint64_t absorber_segments;  /* segments that ended on an absorber                                   */
+  uint64_t mirror_segments;    /* segments that ended on a mirror (the rest are glass)                 */
+  uint64_t reserved[4];
 } prt_counters;
 
 /*
@@ -218,6 +220,13 @@ typedef struct prt_source_desc {
 
 int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_rays, int64_t ray_stride,
                         int64_t first_index, void* cuda_stream);
+
+/*
+ * Measurement aid (no reference counterpart): launches `blocks` x 256 threads that each run
+ * `iters` x 8 independent double-precision FMAs, so the caller can time the FP64 pipe's
+ * FMA rate with CUDA events (flops = blocks*256*iters*16).  d_scratch: >= 1 double.
+ */
+int prt_fp64_probe(double* d_scratch, int32_t blocks, int32_t iters, void* cuda_stream);
 
 #ifdef __cplusplus
 }

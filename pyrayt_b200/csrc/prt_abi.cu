@@ -25,6 +25,7 @@ cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int 
                                  long long n, double* hits, long long* sids, int slots, cudaStream_t st);
 cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
                               long long first, cudaStream_t st);
+cudaError_t prt_launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);
 }
 
 struct prt_scene {
@@ -187,6 +188,13 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
   if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
   cudaError_t e = prt_launch_source(src, d_rays, n_rays, ray_stride, first_index, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "source kernel launch");
+  return PRT_OK;
+}
+
+int prt_fp64_probe(double* d_scratch, int32_t blocks, int32_t iters, void* cuda_stream) {
+  if (!d_scratch || blocks < 1 || iters < 1) return fail(PRT_ERR_INVALID, "bad probe arguments");
+  cudaError_t e = prt_launch_fp64_probe(d_scratch, blocks, iters, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "fp64 probe launch");
   return PRT_OK;
 }
 

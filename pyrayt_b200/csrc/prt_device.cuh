@@ -463,7 +463,7 @@ struct StepOut {
 };
 
 struct StepCounters {
-  unsigned gen, seg, tie, untr, nan, lim;
+  unsigned gen, seg, tie, untr, nan, lim, seg_abs, seg_mir;
 };
 
 // _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
@@ -495,8 +495,10 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
     o.nv1 = 0;
     o.nv2 = 0;
     goes_on = false;  // recorded now, dead next generation (zero direction)
+    c.seg_abs++;
   } else if (L.mat == PRT_MAT_MIRROR) {  // materials.py:58-62, operations.py:105-107
     double n0, n1, n2;
+    c.seg_mir++;
     world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
     const double dots = r.v0 * n0 + r.v1 * n1 + r.v2 * n2;
     o.nv0 = r.v0 - 2 * n0 * dots;

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kTileRays) trace_kernel(const TraceArgs a) {
   const int warp = threadIdx.x >> 5;
 
   RayState rs = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
-  StepCounters sc_ctr = {0, 0, 0, 0, 0, 0};
+  StepCounters sc_ctr = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned c_drop = 0, c_badw = 0;
   if (valid) {
     const double* r = a.rays + i;
@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(kTileRays) trace_kernel(const TraceArgs a) {
   }
 
   // counters: warp-reduce, one atomic per warp and counter
-  unsigned long long vals[9] = {valid ? 1ull : 0ull, sc_ctr.gen, sc_ctr.seg, c_drop, sc_ctr.tie ? 1ull : 0ull,
-                                sc_ctr.untr,         c_badw,     sc_ctr.nan, sc_ctr.lim};
-  unsigned long long* dst[9] = {
+  unsigned long long vals[11] = {valid ? 1ull : 0ull, sc_ctr.gen, sc_ctr.seg, c_drop, sc_ctr.tie ? 1ull : 0ull,
+                                 sc_ctr.untr,         c_badw,     sc_ctr.nan, sc_ctr.lim, sc_ctr.seg_abs,
+                                 sc_ctr.seg_mir};
+  unsigned long long* dst[11] = {
       reinterpret_cast<unsigned long long*>(&a.ctr->rays),
       reinterpret_cast<unsigned long long*>(&a.ctr->generations),
       reinterpret_cast<unsigned long long*>(&a.ctr->segments),
@@ -154,9 +155,11 @@ __global__ void __launch_bounds__(kTileRays) trace_kernel(const TraceArgs a) {
       reinterpret_cast<unsigned long long*>(&a.ctr->untraceable_hits),
       reinterpret_cast<unsigned long long*>(&a.ctr->bad_w),
       reinterpret_cast<unsigned long long*>(&a.ctr->nan_rays),
-      reinterpret_cast<unsigned long long*>(&a.ctr->limit_rays)};
+      reinterpret_cast<unsigned long long*>(&a.ctr->limit_rays),
+      reinterpret_cast<unsigned long long*>(&a.ctr->absorber_segments),
+      reinterpret_cast<unsigned long long*>(&a.ctr->mirror_segments)};
 #pragma unroll
-  for (int q = 0; q < 9; ++q) {
+  for (int q = 0; q < 11; ++q) {
     const unsigned long long s = warp_sum(vals[q]);
     if (lane == 0 && s) atomicAdd(dst[q], s);
   }
@@ -365,6 +368,29 @@ __global__ void source_kernel(const prt_source_desc src, double* rays, long long
   r[12 * stride] = (double)i;
 }
 
+// ---------------------------------------------------------------- FP64 pipe probe (roofline denominator)
+//
+// 8 independent DFMA chains per thread; bench.py times it with CUDA events to get the
+// measured FP64 FMA rate of this GPU (flops = threads * iters * 8 * 2).
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+         a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 0.123456789) out[0] = r;  // keeps the chains alive, never true in practice
+}
+
 }  // namespace prt
 
 // ---------------------------------------------------------------- launchers used by prt_abi.cpp
@@ -425,6 +451,11 @@ cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long lon
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   prt::source_kernel<<<blocks, 256, 0, st>>>(*src, rays, n, stride, first);
+  return cudaGetLastError();
+}
+
+cudaError_t prt_launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st) {
+  prt::fp64_probe_kernel<<<blocks, 256, 0, st>>>(out, iters, 1.0);
   return cudaGetLastError();
 }
 

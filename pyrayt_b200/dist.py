@@ -1,0 +1,106 @@
+"""Multi-GPU plumbing: ray-index-range sharding, one process per GPU (torch.distributed).
+
+Rays never interact, so the trace shards by contiguous ray-index
+range with every rank holding the whole (tiny) scene.  The data path needs exactly
+one exchange: the per-generation row counts of every rank (C1), from which each rank
+knows where its rows sit in the global (generation, id)-ordered frame.  Detector rows
+(C2) can be gathered on request.  Works with NCCL on GPUs and with gloo on CPU tensors
+(the host logic is tested with gloo, world_size 2).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous ray-index range [begin, end) of `rank`; ranges tile [0, n_total) in rank order."""
+    return (n_total * rank) // world, (n_total * (rank + 1)) // world
+
+
+def exchange_counts(gen_counts: np.ndarray, device=None) -> np.ndarray:
+    """C1: all-gather the per-generation row counts. Returns (world, G) int64."""
+    import torch
+    import torch.distributed as dist
+
+    local = torch.as_tensor(np.ascontiguousarray(gen_counts, dtype=np.int64))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local.numpy()[None, :]
+    if device is not None:
+        local = local.to(device)
+    out = [torch.empty_like(local) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, local)
+    return torch.stack(out).cpu().numpy()
+
+
+def global_row_offsets(all_counts: np.ndarray) -> np.ndarray:
+    """First row, in the global (generation, id)-ordered frame, of every (rank, generation) block.
+
+    Global order is generation-major; within a generation ranks follow in rank order because
+    ray-index ranges are assigned in rank order (ids ascending).  Returns (world, G) int64.
+    """
+    all_counts = np.asarray(all_counts, dtype=np.int64)
+    per_gen = all_counts.sum(axis=0)
+    gen_start = np.concatenate(([0], np.cumsum(per_gen)[:-1]))
+    within = np.cumsum(all_counts, axis=0) - all_counts
+    return gen_start[None, :] + within
+
+
+def assemble_global_frame(frames: List[np.ndarray], all_counts: np.ndarray) -> np.ndarray:
+    """Place every rank's (15, rows_r) frame into the global frame (host-side reference of the layout)."""
+    offs = global_row_offsets(all_counts)
+    total = int(np.asarray(all_counts).sum())
+    out = np.empty((15, total))
+    for r, f in enumerate(frames):
+        local_start = np.concatenate(([0], np.cumsum(all_counts[r])[:-1]))
+        for g in range(all_counts.shape[1]):
+            c = int(all_counts[r, g])
+            if c:
+                out[:, offs[r, g]: offs[r, g] + c] = f[:, local_start[g]: local_start[g] + c]
+    return out
+
+
+def gather_rows(local_rows, device=None):
+    """C2: all-gather a variable number of (15, k_r) rows (e.g. the detector rows) to every rank.
+
+    Returns the list of per-rank tensors in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    t = local_rows if isinstance(local_rows, torch.Tensor) else torch.as_tensor(local_rows)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [t]
+    if device is not None:
+        t = t.to(device)
+    world = dist.get_world_size()
+    k = torch.tensor([t.shape[1]], dtype=torch.int64, device=t.device)
+    ks = [torch.empty_like(k) for _ in range(world)]
+    dist.all_gather(ks, k)
+    kmax = int(max(int(x.item()) for x in ks))
+    pad = torch.zeros((t.shape[0], kmax), dtype=t.dtype, device=t.device)
+    pad[:, : t.shape[1]] = t
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return [o[:, : int(kk.item())] for o, kk in zip(outs, ks)]
+
+
+def detector_summary(frame, detector_sid: int, device=None) -> Optional[dict]:
+    """All-reduced spot statistics of the rows that ended on `detector_sid`: count, centroid, RMS radius."""
+    import torch
+    import torch.distributed as dist
+
+    f = frame if isinstance(frame, torch.Tensor) else torch.as_tensor(frame)
+    m = f[5] == float(detector_sid)
+    y, z = f[10][m], f[11][m]
+    acc = torch.stack([m.sum().to(torch.float64), y.sum(), z.sum(), (y * y).sum(), (z * z).sum()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if device is not None:
+            acc = acc.to(device)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    acc = acc.cpu().numpy()
+    if acc[0] == 0:
+        return {"count": 0}
+    cy, cz = acc[1] / acc[0], acc[2] / acc[0]
+    rms = float(np.sqrt(max(0.0, acc[3] / acc[0] - cy * cy + acc[4] / acc[0] - cz * cz)))
+    return {"count": int(acc[0]), "centroid": (float(cy), float(cz)), "rms_radius": rms}

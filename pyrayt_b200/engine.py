@@ -76,10 +76,12 @@ class Engine:
     def _buf(self, key, numel, dtype):
         """Grow-only workspace tensors (the ABI never allocates)."""
         t = self._ws.get(key)
-        if t is None or t.numel() < numel or t.dtype != dtype:
-            self._ws[key] = None
-            t = self._torch.empty(int(numel), dtype=dtype, device=self._dev())
-            self._ws[key] = t
+        if t is not None and t.numel() >= numel and t.dtype == dtype:
+            return t
+        self._ws[key] = None
+        t = None  # drop the old buffer before allocating its replacement
+        t = self._torch.empty(int(numel), dtype=dtype, device=self._dev())
+        self._ws[key] = t
         return t
 
     def release_workspace(self) -> None:
@@ -88,12 +90,14 @@ class Engine:
     # ------------------------------------------------------------------ trace
     def trace(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
               detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
-              host_frame=None, zero_copy: bool = False) -> TraceResult:
+              host_frame=None, zero_copy: bool = False, k1_events=None) -> TraceResult:
         """Trace a device RaySet.
 
         d_rays: torch float64 CUDA tensor (13, N) in the reference RaySet layout.
         to_host: return the frame in pinned host memory (one D2H copy, or with
         ``zero_copy`` the gather kernel writes straight into the pinned buffer).
+        k1_events: optional (start, end) torch CUDA events; ``end`` is recorded right after the
+        trace kernel so a caller can time that kernel alone on the launching stream.
         """
         torch = self._torch
         assert d_rays.is_cuda and d_rays.dtype == torch.float64 and d_rays.dim() == 2
@@ -132,6 +136,8 @@ class Engine:
                 _lib.check(self.lib.prt_trace(self._handle, ctypes.byref(params), d_rays.data_ptr(), n, stride,
                                               ctypes.byref(rec), ctr.data_ptr(), self._stream()), "prt_trace")
                 launches += 1
+                if k1_events is not None:
+                    k1_events[1].record()
                 _lib.check(self.lib.prt_scan_runs(ctypes.byref(rec), G, gen_off.data_ptr(), self._stream()),
                            "prt_scan_runs")
                 launches += 2

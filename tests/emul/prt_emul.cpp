@@ -28,7 +28,7 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
   const prt::SceneView sc = prt::make_view(blob.data());
   long long total = 0;
-  prt::StepCounters c = {0, 0, 0, 0, 0, 0};
+  prt::StepCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long tie_rays = 0;
   for (long long i = 0; i < n; ++i) {
     prt::RayState r;

@@ -1,0 +1,97 @@
+"""Duck-typed stand-ins for the reference's scene objects (the GPU box has no PyRayT tree).
+
+They expose exactly the attributes pyrayt_b200.scene.flatten reads from tinygfx /
+pyrayt objects, so the drop-in RayTracer can be exercised without the reference.
+"""
+import itertools
+
+import numpy as np
+
+_ids = itertools.count(1000)
+
+
+class _AbsorbingMaterial:
+    def trace(self, surface, ray_set):
+        raise NotImplementedError
+
+
+class _ReflectingMaterial(_AbsorbingMaterial):
+    pass
+
+
+class BasicRefractor(_AbsorbingMaterial):
+    def __init__(self, n):
+        self._refractive_index = n
+
+
+class SellmeierRefractor(_AbsorbingMaterial):
+    def __init__(self, b1=0, b2=0, b3=0, c1=0, c2=0, c3=0):
+        self.b1, self.b2, self.b3, self.c1, self.c2, self.c3 = b1, b2, b3, c1, c2, c3
+
+
+class Gooch:  # no trace(): untraceable
+    pass
+
+
+class Sphere:
+    def __init__(self, r):
+        self._radius = r
+
+
+class Plane:
+    def __init__(self, w, l):
+        self._width, self._length = w, l
+
+
+class Cylinder:
+    def __init__(self, r, lo, hi):
+        self._radius, self._h_min, self._h_max, self._capped = r, lo, hi, True
+
+
+class Cube:
+    def __init__(self, lo, hi):
+        self.axis_spans = np.sort(np.vstack((lo, hi)), axis=0).T
+
+
+class Surface:
+    def __init__(self, primitive, material, world=None):
+        self._surface_primitive = primitive
+        self.material = material
+        self._world = np.eye(4) if world is None else np.asarray(world, dtype=float)
+        self._normal_scale = 1
+        self._id = next(_ids)
+
+    def _get_object_transform(self):
+        return np.linalg.inv(self._world)
+
+    def get_id(self):
+        return self._id
+
+    def move_x(self, dx):
+        t = np.eye(4)
+        t[0, 3] = dx
+        self._world = t @ self._world
+        return self
+
+
+class Operation:
+    def __init__(self, value):
+        self.value = value
+
+
+class CSG:
+    def __init__(self, left, right, op, spans):
+        self._l_child, self._r_child, self._operation = left, right, Operation(op)
+        self._aobb = Cube(np.asarray(spans, dtype=float).reshape(3, 2)[:, 0], np.asarray(spans, dtype=float).reshape(3, 2)[:, 1])
+        if op == 3:
+            right._normal_scale = -1
+
+
+class ArraySource:
+    """Source plugin: generate_rays(n) -> (13, n) RaySet array (pyrayt/components.py:481-496)."""
+
+    def __init__(self, rays):
+        self._rays = np.asarray(rays, dtype=float)
+
+    def generate_rays(self, n):
+        return self._rays[:, :n].copy()

@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_shim, sources_np  # noqa: E402
 from pyrayt_b200 import sources as dev_sources  # noqa: E402
+from pyrayt_b200 import workloads  # noqa: E402
 from pyrayt_b200.scene import flatten  # noqa: E402
 
 pyrayt = ref_shim.load()
@@ -76,7 +77,7 @@ def config2_scene():
 
 def config2_tutorial():
     """tutorial condenser lens + aperture stop + detector, filled 10 degree cone, seed 1."""
-    return config2_scene(), cone(4096, 10.0, (-2.04, 0.0, 0.0), 1), 100
+    return config2_scene(), sources_np.from_source(workloads.CONFIG2_SOURCE, 4096), 100
 
 
 def config3_scene():
@@ -112,7 +113,7 @@ def config4_scene():
     return comps
 
 
-CONFIG4_SOURCE = dev_sources.field_fan(seed=4, x_start=-10.0, radius=10.0)
+CONFIG4_SOURCE = workloads.CONFIG4_SOURCE
 
 
 def config4_stack():
@@ -135,7 +136,7 @@ def config5_scene():
     return [parab, pipe, m1, m2, det]
 
 
-CONFIG5_SOURCE = dev_sources.lambertian_cone(seed=5, apex=(0.0, 0.0, 0.0), half_angle_deg=20.0)
+CONFIG5_SOURCE = workloads.CONFIG5_SOURCE
 
 
 def config5_cavity():
@@ -265,6 +266,9 @@ def main(argv):
                             generation_limit=np.int64(gl))
         with open(os.path.join(HERE, name + ".scene.json"), "w") as fh:
             fh.write(scene.to_json())
+        if name.startswith("config"):  # the benchmark workloads also ship with the package
+            with open(os.path.join(ROOT, "pyrayt_b200", "data", name + ".scene.json"), "w") as fh:
+                fh.write(scene.to_json())
         per_ray = frame.shape[1] / max(1, rays.shape[1])
         print(f"{name:28s} rays {rays.shape[1]:6d} rows {frame.shape[1]:7d} ({per_ray:5.2f}/ray) "
               f"leaves {scene.n_leaves:3d} nodes {scene.n_nodes:3d} max gen {int(frame[0].max()) if frame.size else -1}")

@@ -1,0 +1,167 @@
+"""Hand-built flat scenes for tests (no reference objects needed)."""
+import numpy as np
+
+from pyrayt_b200.scene import (FlatScene, MAT_ABSORBER, MAT_GLASS_CONST, MAT_GLASS_SELLMEIER, MAT_MIRROR,
+                               MAT_UNTRACEABLE, NODE_DIFFERENCE, NODE_INTERSECT, NODE_LEAF, NODE_UNION)
+
+SPHERE, PARABOLOID, PLANE, CUBE, CYLINDER = 1, 2, 3, 4, 5
+BIG_BOX = (-1e6, 1e6, -1e6, 1e6, -1e6, 1e6)
+
+
+def translate(x=0.0, y=0.0, z=0.0):
+    m = np.eye(4)
+    m[:3, 3] = (x, y, z)
+    return m
+
+
+def rot_y(deg):
+    a = np.radians(deg)
+    m = np.eye(4)
+    m[0, 0] = m[2, 2] = np.cos(a)
+    m[2, 0] = -np.sin(a)
+    m[0, 2] = np.sin(a)
+    return m
+
+
+def rot_z(deg):
+    a = np.radians(deg)
+    m = np.eye(4)
+    m[0, 0] = m[1, 1] = np.cos(a)
+    m[0, 1] = -np.sin(a)
+    m[1, 0] = np.sin(a)
+    return m
+
+
+class Leaf:
+    def __init__(self, ptype, params, mat=MAT_ABSORBER, matp=(), world=None, sid=None, nscale=1.0):
+        self.ptype, self.params, self.mat, self.matp = ptype, list(params), mat, list(matp)
+        self.world = np.eye(4) if world is None else np.asarray(world, dtype=np.float64)
+        self.sid, self.nscale = sid, nscale
+
+
+class Node:
+    def __init__(self, op, left, right, aabb=BIG_BOX):
+        self.op, self.left, self.right, self.aabb = op, left, right, aabb
+
+
+def union(a, b, aabb=BIG_BOX):
+    return Node(NODE_UNION, a, b, aabb)
+
+
+def intersect(a, b, aabb=BIG_BOX):
+    return Node(NODE_INTERSECT, a, b, aabb)
+
+
+def difference(a, b, aabb=BIG_BOX):
+    return Node(NODE_DIFFERENCE, a, b, aabb)
+
+
+def build(components) -> FlatScene:
+    comp_begin, kind, nleaf, aabb = [0], [], [], []
+    ltype, lobj, lprm, lns, lsid, lmat, lmatp = [], [], [], [], [], [], []
+
+    def emit(o):
+        if isinstance(o, Node):
+            emit(o.left)
+            emit(o.right)
+            kind.append(o.op)
+            nleaf.append(-1)
+            aabb.append(list(o.aabb))
+        else:
+            kind.append(NODE_LEAF)
+            nleaf.append(len(ltype))
+            aabb.append([0.0] * 6)
+            ltype.append(o.ptype)
+            lobj.append(np.linalg.inv(o.world).reshape(16))
+            lprm.append(o.params + [0.0] * (6 - len(o.params)))
+            lns.append(o.nscale)
+            lsid.append(100 + len(lsid) if o.sid is None else o.sid)
+            lmat.append(o.mat)
+            lmatp.append(o.matp + [0.0] * (6 - len(o.matp)))
+
+    for c in components:
+        emit(c)
+        comp_begin.append(len(kind))
+    obj = np.asarray(lobj, dtype=np.float64).reshape(-1, 16)
+    obj[:, 12:15] = 0.0
+    obj[:, 15] = 1.0
+    s = FlatScene(
+        comp_node_begin=np.asarray(comp_begin, dtype=np.int32), node_kind=np.asarray(kind, dtype=np.int32),
+        node_leaf=np.asarray(nleaf, dtype=np.int32), node_aabb=np.asarray(aabb, dtype=np.float64).reshape(-1, 6),
+        leaf_type=np.asarray(ltype, dtype=np.int32), leaf_obj=obj,
+        leaf_param=np.asarray(lprm, dtype=np.float64).reshape(-1, 6), leaf_nscale=np.asarray(lns, dtype=np.float64),
+        leaf_sid=np.asarray(lsid, dtype=np.int64), leaf_mat=np.asarray(lmat, dtype=np.int32),
+        leaf_matp=np.asarray(lmatp, dtype=np.float64).reshape(-1, 6))
+    s.validate()
+    return s
+
+
+def make_rays(origins, directions, wavelength=0.633, index=1.0, intensity=100.0):
+    """(13,N) RaySet array (pyrayt/_pyrayt.py:13-44) from (N,3) origins / directions."""
+    o = np.atleast_2d(np.asarray(origins, dtype=np.float64))
+    d = np.atleast_2d(np.asarray(directions, dtype=np.float64))
+    n = o.shape[0]
+    r = np.zeros((13, n))
+    r[0:3] = o.T
+    r[3] = 1
+    r[4:7] = d.T
+    r[9] = intensity
+    r[10] = wavelength
+    r[11] = index
+    r[12] = np.arange(n)
+    return r
+
+
+def random_scene_and_rays(seed, n_rays=512):
+    """A random but valid scene exercising every primitive / operation / material."""
+    rng = np.random.default_rng(seed)
+    glass = dict(mat=MAT_GLASS_CONST, matp=[1.5])
+    bk7 = dict(mat=MAT_GLASS_SELLMEIER, matp=[1.03961212, 0.231792344, 1.01046945, 6.00069867e-3, 2.00179144e-2, 103.560653])
+
+    def pose():
+        return translate(*rng.uniform(-3, 3, 3)) @ rot_z(rng.uniform(0, 360)) @ rot_y(rng.uniform(0, 360))
+
+    def prim(kw):
+        t = int(rng.integers(1, 6))
+        if t == SPHERE:
+            return Leaf(SPHERE, [rng.uniform(0.5, 1.5)], world=pose(), **kw)
+        if t == PARABOLOID:
+            return Leaf(PARABOLOID, [rng.uniform(0.3, 1.0), rng.uniform(0.5, 2.0)], world=pose(), **kw)
+        if t == PLANE:
+            return Leaf(PLANE, [rng.uniform(1, 3), rng.uniform(1, 3)], world=pose(), **kw)
+        if t == CUBE:
+            lo = -rng.uniform(0.3, 1.2, 3)
+            hi = rng.uniform(0.3, 1.2, 3)
+            return Leaf(CUBE, [lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]], world=pose(), **kw)
+        return Leaf(CYLINDER, [rng.uniform(0.3, 1.0), -rng.uniform(0.3, 1.5), rng.uniform(0.3, 1.5), 1.0], world=pose(), **kw)
+
+    mats = [glass, bk7, dict(mat=MAT_MIRROR), dict(mat=MAT_ABSORBER)]
+    comps = []
+    for _ in range(int(rng.integers(3, 7))):
+        kw = mats[int(rng.integers(0, len(mats)))]
+        shape = int(rng.integers(0, 4))
+        ops = (union, intersect, difference)
+        if shape == 0:
+            comps.append(prim(kw))
+        elif shape == 1:
+            comps.append(ops[int(rng.integers(0, 3))](prim(kw), prim(kw)))
+        elif shape == 2:
+            comps.append(ops[int(rng.integers(0, 3))](ops[int(rng.integers(0, 3))](prim(kw), prim(kw)), prim(kw)))
+        else:  # right-nested
+            comps.append(ops[int(rng.integers(0, 3))](prim(kw), ops[int(rng.integers(0, 3))](prim(kw), prim(kw))))
+    # enclose in absorbing walls so most rays end on something
+    for ax in range(3):
+        for sgn in (-1, 1):
+            w = np.eye(4)
+            if ax == 0:
+                w = rot_y(90)
+            elif ax == 1:
+                w = rot_z(90) @ rot_y(90)
+            w = translate(*(np.eye(3)[ax] * sgn * 8)) @ w
+            comps.append(Leaf(PLANE, [20, 20], world=w, mat=MAT_ABSORBER))
+    o = rng.uniform(-5, 5, (n_rays, 3))
+    d = rng.normal(size=(n_rays, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = make_rays(o, d)
+    rays[10] = rng.uniform(0.45, 0.7, n_rays)
+    return build(comps), rays

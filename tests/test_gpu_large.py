@@ -1,0 +1,224 @@
+"""GPU parity at BASELINE sizes: oracle comparison where the CPU finishes in seconds,
+size-independent properties at the full ray counts."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import assert_frames_match, load_case
+
+pytestmark = pytest.mark.gpu
+THREADS = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def torch_mod(cuda_device):
+    import torch
+
+    return torch
+
+
+def _engine(name):
+    import pyrayt_b200
+    from pyrayt_b200 import workloads
+
+    wl = workloads.WORKLOADS[name]
+    return wl, pyrayt_b200.Engine(wl.scene(), device=0)
+
+
+@pytest.mark.parametrize("name,n", [("config2", 100_000), ("config4", 1 << 17), ("config5", 1 << 16)])
+def test_workload_matches_oracle_bit_for_bit(name, n, torch_mod):
+    from oracle import oracle, sources_np
+
+    wl, eng = _engine(name)
+    d_rays = wl.source.generate(n, device=0)
+    h_rays = sources_np.from_source(wl.source, n)
+    assert np.array_equal(d_rays.cpu().numpy(), h_rays), "device source differs from its NumPy restatement"
+    res = eng.trace(d_rays, generation_limit=wl.generation_limit, to_host=True)
+    want, octr = oracle.trace(wl.scene(), h_rays, wl.generation_limit, threads=THREADS)
+    got = res.frame.numpy()
+    assert_frames_match(got, want, what=name)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert res.counters["generations"] == octr["generations"]
+    assert res.ray_surface_tests == octr["generations"] * wl.scene().n_leaves
+
+
+def test_config3_prism_one_million_rays(torch_mod):
+    """examples/chromatic_dispersion.py geometry, 11 wavelengths x 95,326 rays (= 1,048,586)."""
+    import pyrayt_b200
+    from oracle import oracle
+
+    scene, rays_small, _, gl = load_case("config3_prism")
+    per = 95_326
+    lam = np.linspace(0.44, 0.75, 11)
+    # LineOfRays(spacing=0.1).move_x(-0.5).rotate_y(-3): rebuild from the golden rays' two end points per source
+    blocks = []
+    for k in range(11):
+        src = rays_small[:, k * 96:(k + 1) * 96]
+        t = np.linspace(0.0, 1.0, per)
+        blk = np.repeat(src[:, :1], per, axis=1)
+        blk[0:3] = src[0:3, :1] + (src[0:3, -1:] - src[0:3, :1]) * t
+        blk[10] = lam[k]
+        blocks.append(blk)
+    rays = np.ascontiguousarray(np.hstack(blocks))
+    rays[12] = np.arange(rays.shape[1])
+    assert rays.shape[1] == 1_048_586
+    eng = pyrayt_b200.Engine(scene, device=0)
+    res = eng.trace(torch_mod.from_numpy(rays).cuda(), generation_limit=gl, to_host=True)
+    want, _ = oracle.trace(scene, rays, gl, threads=THREADS)
+    assert np.array_equal(res.frame.numpy(), want, equal_nan=True)
+    # dispersion: shorter wavelengths leave the prism at a steeper angle
+    last = res.frame.numpy()[:, res.frame.numpy()[0] == 2]
+    tilt = [last[14, last[2] == w].mean() for w in lam]
+    assert np.all(np.diff(tilt) > 0) or np.all(np.diff(tilt) < 0)
+
+
+def test_config4_full_size_properties(torch_mod):
+    """2^24 rays: row order, monotone survival, per-ray generation prefixes, strided oracle sample."""
+    from oracle import oracle, sources_np
+
+    torch = torch_mod
+    wl, eng = _engine("config4")
+    n = wl.n_rays
+    d_rays = wl.source.generate(n, device=0)
+    res = eng.trace(d_rays, generation_limit=wl.generation_limit)
+    f = res.frame
+    assert res.rows == f.shape[1] == res.counters["segments"] and res.counters["rows_dropped"] == 0
+    gen, rid = f[0], f[4]
+    # rows ordered by (generation, id): the key must be strictly increasing
+    key = gen * float(1 << 26) + rid
+    assert bool((key[1:] > key[:-1]).all())
+    # survivors only shrink, and generation g rows are exactly gen_counts[g]
+    gc = res.gen_counts
+    assert np.all(np.diff(gc) <= 0) and gc.sum() == res.rows
+    cnt = torch.bincount(gen.to(torch.int64), minlength=len(gc)).cpu().numpy()
+    assert np.array_equal(cnt[: len(gc)], gc)
+    # every ray's rows are generations 0..k-1 with no gaps: sum of generations == k(k-1)/2 per ray
+    k = torch.bincount(rid.to(torch.int64), minlength=n)
+    gs = torch.zeros(n, dtype=torch.float64, device=f.device).index_add_(0, rid.to(torch.int64), gen)
+    assert bool((gs == (k * (k - 1) / 2).to(torch.float64)).all())
+    # strided sample of 2048 rays against the oracle, bit for bit
+    idx = np.arange(0, n, n // 2048)
+    h = np.hstack([sources_np.from_source(wl.source, 1, first_index=int(i)) for i in idx])
+    want, _ = oracle.trace(wl.scene(), h, wl.generation_limit, threads=THREADS)
+    sel = torch.isin(rid, torch.from_numpy(idx.astype(np.float64)).to(f.device))
+    got = f[:, sel].cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True)
+    del f, res
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+
+
+def test_sharded_ranges_reassemble_the_monolithic_frame(torch_mod):
+    """tracing ray-index ranges separately and placing the blocks by the all-gathered
+    counts gives the single-GPU frame bit for bit."""
+    from pyrayt_b200 import dist as pdist
+
+    wl, eng = _engine("config4")
+    n = 1 << 18
+    d_rays = wl.source.generate(n, device=0)
+    whole = eng.trace(d_rays, generation_limit=wl.generation_limit, to_host=True)
+    parts, counts = [], []
+    for r in range(4):
+        b, e = pdist.shard_range(n, r, 4)
+        shard = wl.source.generate(e - b, device=0, first_index=b)
+        assert torch_mod.equal(shard, d_rays[:, b:e])
+        res = eng.trace(shard, generation_limit=wl.generation_limit, to_host=True)
+        parts.append(res.frame.numpy())
+        counts.append(res.gen_counts)
+    glob = pdist.assemble_global_frame(parts, np.stack(counts))
+    assert np.array_equal(glob, whole.frame.numpy(), equal_nan=True)
+
+
+def test_record_modes_overflow_retry_and_zero_copy(torch_mod):
+    wl, eng = _engine("config4")
+    n = 1 << 16
+    d_rays = wl.source.generate(n, device=0)
+    G = wl.generation_limit
+    full = eng.trace(d_rays, generation_limit=G, to_host=True)
+    f = full.frame.numpy()
+    det = int(wl.scene().leaf_sid[-1])
+    only = eng.trace(d_rays, generation_limit=G, record="surface", detector_sid=det, to_host=True)
+    assert np.array_equal(only.frame.numpy(), f[:, f[5] == det])
+    none = eng.trace(d_rays, generation_limit=G, record="none")
+    for k in ("rays", "generations", "segments", "limit_rays", "absorber_segments"):
+        assert none.counters[k] == full.counters[k]
+    tiny = eng.trace(d_rays, generation_limit=G, capacity=1000, to_host=True)  # forces the overflow retry
+    assert np.array_equal(tiny.frame.numpy(), f)
+    zc = eng.trace(d_rays, generation_limit=G, to_host=True, zero_copy=True)
+    assert np.array_equal(zc.frame.numpy(), f)
+
+
+def test_component_intersect_matches_oracle(torch_mod):
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+
+    for seed in range(4):
+        scene, rays = su.random_scene_and_rays(200 + seed, n_rays=1000)
+        eng = pyrayt_b200.Engine(scene, device=0)
+        r = np.zeros((8, rays.shape[1]))
+        r[0:3], r[3], r[4:7] = rays[0:3], 1, rays[4:7]
+        d = torch_mod.from_numpy(r).cuda()
+        for c in range(scene.n_components):
+            h, s = eng.intersect(c, d)
+            oh, osid = oracle.intersect(scene, c, r)
+            assert np.array_equal(h.cpu().numpy(), oh)
+            fin = np.isfinite(oh)
+            assert np.array_equal(s.cpu().numpy()[fin], osid[fin])
+
+
+def test_random_scenes_match_oracle(torch_mod):
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+
+    for seed in range(12):
+        scene, rays = su.random_scene_and_rays(seed, n_rays=4096)
+        eng = pyrayt_b200.Engine(scene, device=0)
+        res = eng.trace(torch_mod.from_numpy(rays).cuda(), generation_limit=16, to_host=True)
+        want, _ = oracle.trace(scene, rays, 16, threads=THREADS)
+        assert np.array_equal(res.frame.numpy(), want, equal_nan=True), seed
+
+
+def test_drop_in_raytracer_api(torch_mod):
+    """pyrayt.RayTracer's public surface (pyrayt/_pyrayt.py:211-354) on duck-typed components."""
+    import pandas as pd
+
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import fakes, scene_util as su
+
+    glass = fakes.BasicRefractor(1.5)
+    lens = fakes.CSG(fakes.Surface(fakes.Sphere(2.0), glass, su.translate(1.9, 0, 0)),
+                     fakes.Surface(fakes.Sphere(2.0), glass, su.translate(-1.9, 0, 0)), 2, (-0.1, 0.1, -1, 1, -1, 1))
+    det = fakes.Surface(fakes.Plane(4, 4), fakes._AbsorbingMaterial(), su.translate(3, 0, 0) @ su.rot_y(90))
+    ys = np.linspace(-0.3, 0.3, 21)
+    rays = su.make_rays(np.stack([np.full(21, -3.0), ys, np.zeros(21)], 1), np.tile([1.0, 0, 0], (21, 1)))
+    tracer = pyrayt_b200.RayTracer(fakes.ArraySource(rays), [lens, det], rays_per_source=21, generation_limit=10)
+    df = tracer.trace()
+    assert isinstance(df, pd.DataFrame) and list(df.columns) == list(pyrayt_b200.FRAME_COLUMNS)
+    assert all(dt == np.float64 for dt in df.dtypes) and df.shape == (63, 15)
+    assert isinstance(df.index, pd.RangeIndex)
+    want, _ = oracle.trace(pyrayt_b200.flatten([lens, det]), rays, 10)
+    assert np.array_equal(df.to_numpy().T, want)
+    assert tracer.get_results() is df
+    tracer.calculate_source_ids()
+    assert "source_id" in tracer.get_results().columns
+    # components are held by reference: moving one changes the next trace
+    det.move_x(1.0)
+    df2 = tracer.trace()
+    assert np.allclose(df2["x1"][df2["generation"] == 2], 4.0)
+    # setters / getters
+    tracer.set_rays_per_source(5)
+    tracer.set_generation_limit(1)
+    assert tracer.get_rays_per_source() == 5 and tracer.get_generation_limit() == 1
+    assert tracer.trace().shape == (5, 15)
+    # a trace with no hit returns the reference's empty float32 frame
+    away = su.make_rays([[0, 0, 10.0]], [[0, 0, 1.0]])
+    empty = pyrayt_b200.RayTracer(fakes.ArraySource(away), [det], rays_per_source=1).trace()
+    assert empty.shape == (0, 15) and all(dt == np.float32 for dt in empty.dtypes)
+    # hitting a surface without a traceable material raises like the reference (AttributeError)
+    bad = fakes.Surface(fakes.Sphere(1.0), fakes.Gooch(), su.translate(0, 0, 13))
+    with pytest.raises(AttributeError):
+        pyrayt_b200.RayTracer(fakes.ArraySource(away), [bad], rays_per_source=1).trace()

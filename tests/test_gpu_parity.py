@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, assert_frames_match, load_case
+from tests.helpers import GOLDEN_CASES, assert_frames_match, load_case
 
 pytestmark = pytest.mark.gpu
 
