@@ -199,6 +199,8 @@ class FlatScene:
                 kw[k] = np.asarray(v, dtype=dt[k])
             else:
                 kw[k] = np.asarray([float.fromhex(x) for x in v], dtype=np.float64)
+        for k, w in (("node_aabb", 6), ("leaf_obj", 16), ("leaf_param", 6), ("leaf_matp", 6)):
+            kw[k] = kw[k].reshape(-1, w)
         s = cls(**kw)
         s.validate()
         return s

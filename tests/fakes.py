@@ -10,21 +10,25 @@ import numpy as np
 _ids = itertools.count(1000)
 
 
-class _AbsorbingMaterial:
+class TracableMaterial:
     def trace(self, surface, ray_set):
         raise NotImplementedError
 
 
-class _ReflectingMaterial(_AbsorbingMaterial):
+class _AbsorbingMaterial(TracableMaterial):
     pass
 
 
-class BasicRefractor(_AbsorbingMaterial):
+class _ReflectingMaterial(TracableMaterial):
+    pass
+
+
+class BasicRefractor(TracableMaterial):
     def __init__(self, n):
         self._refractive_index = n
 
 
-class SellmeierRefractor(_AbsorbingMaterial):
+class SellmeierRefractor(TracableMaterial):
     def __init__(self, b1=0, b2=0, b3=0, c1=0, c2=0, c3=0):
         self.b1, self.b2, self.b3, self.c1, self.c2, self.c3 = b1, b2, b3, c1, c2, c3
 
