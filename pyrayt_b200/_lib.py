@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpyrayt_b200.so")
+LIB_PATH = os.environ.get("PYRAYT_B200_LIB") or os.path.join(_HERE, "libpyrayt_b200.so")  # override: experiments only
 
 ABI_VERSION = 1
 FRAME_COLS = 15

@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/pyrayt_b200.h"
 #include "prt_scene.h"
@@ -36,6 +37,66 @@ PRT_HD void sort2(double& a, double& b) {
   }
 }
 
+// ---------------------------------------------------------------- exact division by a shared reciprocal
+//
+// Many quotients of one ray share a denominator (the two roots of a quadratic, the two faces
+// of a slab, every bounding box of the scene against the same world-space direction).  With
+// r = RN(1/b) the sequence q = RN(a*r); e = fma(-b, q, a); q' = fma(e, r, q) yields RN(a/b)
+// (Markstein's theorem), i.e. bit-for-bit what the reference's true division gives, for 3 FP64
+// instructions per quotient instead of a full IEEE division.  Denominators outside a safe range
+// (and numerators that could make the residual inexact) fall back to a real division.
+struct Rcp {
+  double b, r;
+  unsigned lim;  // width of the numerator-exponent window in which the 3-instruction form is exact (0: never)
+};
+
+PRT_HD unsigned hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned)__double2hiint(x);
+#else
+  unsigned long long u;
+  memcpy(&u, &x, 8);
+  return (unsigned)(u >> 32);
+#endif
+}
+// biased exponent of x (0 for zero/denormals, 2047 for inf/NaN)
+PRT_HD unsigned exp_of(double x) { return (hi_word(x) >> 20) & 0x7ffu; }
+
+constexpr unsigned kExpLo = 123;          // 2^-900
+constexpr unsigned kExpSpan = 1923 - 123;  // up to 2^900
+
+PRT_HD Rcp make_rcp(double b) {
+  Rcp R;
+  R.b = b;
+  R.lim = (exp_of(b) - kExpLo < kExpSpan) ? kExpSpan : 0u;  // |b| in [2^-900, 2^900), finite
+#if defined(__CUDA_ARCH__)
+  R.r = __drcp_rn(b);
+#else
+  R.r = 1.0 / b;
+#endif
+  return R;
+}
+
+// RN(a / R.b) without guards; exact when a is 0 or has |a| in [2^-900, 2^900) and R.lim != 0
+PRT_HD double div_fast(double a, const Rcp& R) {
+  const double q = a * R.r;
+  const double e = fma(-R.b, q, a);
+  return fma(e, R.r, q);
+}
+
+PRT_HD double div_by(double a, const Rcp& R) {
+  if (!(exp_of(a) - kExpLo < R.lim)) return a / R.b;  // zero, tiny, huge, inf, NaN or an unsafe denominator
+  return div_fast(a, R);
+}
+
+// per-generation reciprocals of a ray direction, shared by every bounding-box test against it
+struct RayInv {
+  Rcp r0, r1, r2;
+  bool z0, z1, z2;
+  bool fast;       // guard-free slab arithmetic is provably exact for this ray (see cube_hits)
+  int s0, s1, s2;  // per axis: 0 if the ray runs towards +axis (near face = lo) else 1
+};
+
 struct SceneView {
   const BlobHeader* h;
   const int* comp;
@@ -60,9 +121,9 @@ PRT_HD SceneView make_view(const unsigned char* blob) {
 PRT_HD void clip_z(double s0, double s1, double zlo, double zhi, double oz, double dz,
                                        double b0_num, double& t0, double& t1) {
   const bool par = isz(dz);
-  const double den = dz + (par ? 1.0 : 0.0);
-  double b0 = b0_num / den;
-  double b1 = (zhi - oz) / den;
+  const Rcp den = make_rcp(dz + (par ? 1.0 : 0.0));
+  double b0 = div_by(b0_num, den);
+  double b1 = div_by(zhi - oz, den);
   if (par) {
     b0 = ((oz >= zlo) && (oz <= zhi)) ? -PRT_INF : PRT_INF;
     b1 = PRT_INF;
@@ -80,29 +141,65 @@ PRT_HD void clip_z(double s0, double s1, double zlo, double zhi, double oz, doub
 }
 
 // one slab of Cube.intersect (primitives.py:531-565)
-PRT_HD void cube_axis(double o, double d, double lo, double hi, double& mn, double& mx) {
-  const bool zf = isz(d);
-  const double den = d + (zf ? 1.0 : 0.0);
-  double h0 = -(o - lo) / den;
-  double h1 = -(o - hi) / den;
-  if (zf) {
-    h0 = (o <= hi && o >= lo) ? -PRT_INF : PRT_INF;
-    h1 = PRT_INF;
+PRT_HD void cube_axis(double o, bool zf, const Rcp& den, double lo, double hi, double& mn, double& mx) {
+  if (zf) {  // ray parallel to the slab: (-inf, +inf) inside, (+inf, +inf) outside
+    mn = (o <= hi && o >= lo) ? -PRT_INF : PRT_INF;
+    mx = PRT_INF;
+    return;
   }
+  double h0 = div_by(-(o - lo), den);
+  double h1 = div_by(-(o - hi), den);
   sort2(h0, h1);
   mn = h0;
   mx = h1;
 }
 
+// a coordinate / span for which o - s is 0 or at least 2^-900 in magnitude
+PRT_HD bool tame(double x) { return x == 0.0 || (exp_of(x) - 200u < 1700u - 200u); }  // 0 or [2^-823, 2^677)
+
+// reciprocals of the direction of a ray starting at (o0,o1,o2); `boxes_tame`: every box this
+// ray will be tested against has spans that are 0 or in [2^-823, 2^677) (BlobHeader.flags & 1)
+PRT_HD RayInv make_ray_inv(double o0, double o1, double o2, double d0, double d1, double d2, bool boxes_tame) {
+  RayInv I;
+  I.z0 = isz(d0);
+  I.z1 = isz(d1);
+  I.z2 = isz(d2);
+  const double e0 = d0 + (I.z0 ? 1.0 : 0.0), e1 = d1 + (I.z1 ? 1.0 : 0.0), e2 = d2 + (I.z2 ? 1.0 : 0.0);
+  I.r0 = make_rcp(e0);
+  I.r1 = make_rcp(e1);
+  I.r2 = make_rcp(e2);
+  I.s0 = e0 < 0 ? 1 : 0;
+  I.s1 = e1 < 0 ? 1 : 0;
+  I.s2 = e2 < 0 ? 1 : 0;
+  // Fast slab form: differences of tame numbers are 0 or >= 2^-876 and < 2^678, denominators are in
+  // [2^-66, 2^66) -> every quotient and its FMA residual stay normal, so div_fast is exact.
+  const bool den_ok = (exp_of(e0) - 957u < 132u) && (exp_of(e1) - 957u < 132u) && (exp_of(e2) - 957u < 132u);
+  I.fast = boxes_tame && !I.z0 && !I.z1 && !I.z2 && den_ok && tame(o0) && tame(o1) && tame(o2);
+  return I;
+}
+
 // Cube.intersect (primitives.py:516-581); also every CSG node's world-space AABB (csg.py:126-128)
-PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, double d0, double d1,
-                                          double d2, double& t0, double& t1) {
-  double mn0, mx0, mn1, mx1, mn2, mx2;
-  cube_axis(o0, d0, sp[0], sp[1], mn0, mx0);
-  cube_axis(o1, d1, sp[2], sp[3], mn1, mx1);
-  cube_axis(o2, d2, sp[4], sp[5], mn2, mx2);
-  const double lo = fmax(fmax(mn0, mn1), mn2);
-  const double hi = fmin(fmin(mx0, mx1), mx2);
+PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, const RayInv& I, double& t0,
+                      double& t1) {
+  double lo, hi;
+  if (I.fast) {
+    // the sign of the direction says which face is the near one: no sort, no parallel-ray cases;
+    // values are bit-identical to the generic path (rounding is monotonic)
+    const double mn0 = div_fast(-(o0 - sp[I.s0]), I.r0), mx0 = div_fast(-(o0 - sp[1 - I.s0]), I.r0);
+    const double mn1 = div_fast(-(o1 - sp[2 + I.s1]), I.r1), mx1 = div_fast(-(o1 - sp[3 - I.s1]), I.r1);
+    const double mn2 = div_fast(-(o2 - sp[4 + I.s2]), I.r2), mx2 = div_fast(-(o2 - sp[5 - I.s2]), I.r2);
+    lo = mn0 > mn1 ? mn0 : mn1;
+    lo = lo > mn2 ? lo : mn2;
+    hi = mx0 < mx1 ? mx0 : mx1;
+    hi = hi < mx2 ? hi : mx2;
+  } else {
+    double mn0, mx0, mn1, mx1, mn2, mx2;
+    cube_axis(o0, I.z0, I.r0, sp[0], sp[1], mn0, mx0);
+    cube_axis(o1, I.z1, I.r1, sp[2], sp[3], mn1, mx1);
+    cube_axis(o2, I.z2, I.r2, sp[4], sp[5], mn2, mx2);
+    lo = fmax(fmax(mn0, mn1), mn2);
+    hi = fmin(fmin(mx0, mx1), mx2);
+  }
   if (lo < hi) {
     t0 = lo;
     t1 = hi;
@@ -116,9 +213,9 @@ PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, double 
 PRT_HD void plane_axis(double o, double d, double dim, double& mn, double& mx) {
   const bool zf = isz(d);
   const double half = dim / 2;
-  const double den = d + (zf ? 1.0 : 0.0);
-  double v0 = -(o - half) / den;
-  double v1 = -(o + half) / den;
+  const Rcp den = make_rcp(d + (zf ? 1.0 : 0.0));
+  double v0 = div_by(-(o - half), den);
+  double v1 = div_by(-(o + half), den);
   if (zf) {
     v0 = (fabs(o) <= half) ? -PRT_INF : PRT_INF;
     v1 = PRT_INF;
@@ -146,9 +243,9 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double c = (o0 * o0 + o1 * o1 + o2 * o2) - r * r;
       const double disc = b * b - 4 * a * c;
       const double root = sqrt(fmax(0.0, disc));
-      const double den = 2 * a;
-      t0 = (-b + root) / den;
-      t1 = (-b - root) / den;
+      const Rcp den = make_rcp(2 * a);
+      t0 = div_by(-b + root, den);
+      t1 = div_by(-b - root, den);
       if (!(disc >= 0)) {
         t0 = PRT_INF;
         t1 = PRT_INF;
@@ -163,9 +260,9 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double disc = b * b - 4 * a * c;
       const bool lin = isz(a);
       const double root = sqrt(fmax(0.0, disc));
-      const double den = 2 * a + (lin ? 1.0 : 0.0);
-      double s0 = (-b + root) / den;
-      double s1 = (-b - root) / den;
+      const Rcp den = make_rcp(2 * a + (lin ? 1.0 : 0.0));
+      double s0 = div_by(-b + root, den);
+      double s1 = div_by(-b - root, den);
       if (!(disc >= 0)) {
         s0 = PRT_INF;
         s1 = PRT_INF;
@@ -190,9 +287,9 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double disc = b * b - 4 * a * c;
       const bool lin = isz(a);
       const double root = sqrt(fmax(0.0, disc));
-      const double den = 2 * a + (lin ? 1.0 : 0.0);
-      double s0 = (-b + root) / den;
-      double s1 = (-b - root) / den;
+      const Rcp den = make_rcp(2 * a + (lin ? 1.0 : 0.0));
+      double s0 = div_by(-b + root, den);
+      double s1 = div_by(-b - root, den);
       if (!(disc >= 0)) {
         s0 = PRT_INF;
         s1 = PRT_INF;
@@ -218,7 +315,7 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       t1 = t;
     } break;
     case PRT_CUBE:  // primitives.py:516-581
-      cube_hits(L.prm, o0, o1, o2, d0, d1, d2, t0, t1);
+      cube_hits(L.prm, o0, o1, o2, make_ray_inv(o0, o1, o2, d0, d1, d2, false), t0, t1);
       break;
     default:
       t0 = PRT_INF;
@@ -364,21 +461,29 @@ PRT_HD void merge_lists(HitStack& S, int lvl, int op, int nR, GetRT r_t, GetRL r
 }
 
 // component.intersect for one ray: runs ops [begin, end); the result is level 0 of S.
-PRT_HD void eval_component(const SceneView& sc, int begin, int end, double p0, double p1,
-                                               double p2, double v0, double v1, double v2, HitStack& S,
-                                               bool& tie) {
+//
+// `best_t` enables the exact pruning of whole components: when the encoder has proven that the
+// root bounding box contains the solid (Op.c & 1, see prt_encode.h) a component whose box lies
+// entirely behind the ray, or entirely beyond the nearest hit found so far, cannot change the
+// result of _st_propagate and is skipped (returns false).  prune = false evaluates everything
+// (component.intersect must also report the hits behind the ray).
+PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, double p1, double p2, double v0,
+                           double v1, double v2, const RayInv& inv, bool prune, double best_t, HitStack& S,
+                           bool& tie) {
   int sp = 0;
   int pc = begin;
   while (pc < end) {
     const Op op = sc.ops[pc];
     if (op.kind == OP_ENTER) {
       double b0, b1;
-      cube_hits(sc.aabb + 6 * op.a, p0, p1, p2, v0, v1, v2, b0, b1);
+      cube_hits(sc.aabb + 6 * op.a, p0, p1, p2, inv, b0, b1);
       if (!(b0 < PRT_INF)) {  // cube_hits returns finite values or (+inf,+inf): csg.py:126-128
+        if (pc == begin) return false;  // root culled: no hits at all
         S.len[sp++] = 0;
         pc = op.b;
         continue;
       }
+      if (prune && pc == begin && (op.c & 1) && (b1 < -kCullMargin || b0 > best_t + kCullMargin)) return false;
     } else if (op.kind == OP_LEAF) {
       double t0, t1;
       leaf_hits(sc.leaves[op.a], p0, p1, p2, v0, v1, v2, t0, t1);
@@ -406,6 +511,7 @@ PRT_HD void eval_component(const SceneView& sc, int begin, int end, double p0, d
     }
     ++pc;
   }
+  return true;
 }
 
 // nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386)
@@ -414,6 +520,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
                                             bool& tie) {
   best_t = PRT_INF;
   best_leaf = -1;
+  const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
   const int nc = sc.h->n_components;
   for (int c = 0; c < nc; ++c) {
     const int begin = sc.comp[c], end = sc.comp[c + 1];
@@ -430,7 +537,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
       continue;
     }
     S.flags = 0;
-    eval_component(sc, begin, end, p0, p1, p2, v0, v1, v2, S, tie);
+    if (!eval_component(sc, begin, end, p0, p1, p2, v0, v1, v2, inv, true, best_t, S, tie)) continue;
     const int b = buf_of(S, 0);
     const int n = S.len[0];
     for (int k = 0; k < n; ++k) {  // sorted: the first positive entry is the argmin of where(hits>0)

@@ -1,6 +1,7 @@
 // Host-side scene encoder: caller's postfix CSG programs (prt_scene_desc) -> the blob the
 // kernels stage in shared memory (prt_scene.h).  Shared by the ABI layer and tests/emul.
 #pragma once
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,52 @@ struct TreeNode {
   int l = -1, r = -1;
   int slots = 2;
 };
+
+// axis-aligned box used to prove that a caller-supplied bounding box contains its solid
+struct Box3 {
+  double lo[3], hi[3];
+  bool empty;
+};
+
+// world-space bounds of leaf l: the primitive's object-space bounding cube (primitives.py
+// bounding_points :225,:312,:431,:512,:635) pushed through the inverse of the object matrix
+inline bool leaf_world_box(const prt_scene_desc* d, int l, Box3& out) {
+  const double* M = d->leaf_obj + 16 * l;
+  const double* p = d->leaf_param + 6 * l;
+  double lo[3], hi[3];
+  switch (d->leaf_type[l]) {
+    case PRT_SPHERE: for (int k = 0; k < 3; ++k) { lo[k] = -std::fabs(p[0]); hi[k] = std::fabs(p[0]); } break;
+    case PRT_PARABOLOID: {
+      const double r = std::sqrt(4 * p[0] * p[1]);
+      lo[0] = lo[1] = -r; hi[0] = hi[1] = r; lo[2] = 0; hi[2] = p[1];
+    } break;
+    case PRT_PLANE: lo[0] = -p[0] / 2; hi[0] = p[0] / 2; lo[1] = -p[1] / 2; hi[1] = p[1] / 2; lo[2] = hi[2] = 0; break;
+    case PRT_CUBE: for (int k = 0; k < 3; ++k) { lo[k] = p[2 * k]; hi[k] = p[2 * k + 1]; } break;
+    case PRT_CYLINDER: lo[0] = lo[1] = -std::fabs(p[0]); hi[0] = hi[1] = std::fabs(p[0]); lo[2] = p[1]; hi[2] = p[2]; break;
+    default: return false;
+  }
+  // invert the affine object matrix: W = A^-1, t_w = -A^-1 t
+  const double a = M[0], b = M[1], c = M[2], e = M[4], f = M[5], g = M[6], h = M[8], i = M[9], j = M[10];
+  const double det = a * (f * j - g * i) - b * (e * j - g * h) + c * (e * i - f * h);
+  if (!(std::fabs(det) > 1e-300) || !std::isfinite(det)) return false;
+  const double W[9] = {(f * j - g * i) / det, (c * i - b * j) / det, (b * g - c * f) / det,
+                       (g * h - e * j) / det, (a * j - c * h) / det, (c * e - a * g) / det,
+                       (e * i - f * h) / det, (b * h - a * i) / det, (a * f - b * e) / det};
+  const double t[3] = {M[3], M[7], M[11]};
+  out.empty = false;
+  for (int k = 0; k < 3; ++k) { out.lo[k] = INFINITY; out.hi[k] = -INFINITY; }
+  for (int corner = 0; corner < 8; ++corner) {
+    const double q[3] = {((corner & 1) ? hi[0] : lo[0]) - t[0], ((corner & 2) ? hi[1] : lo[1]) - t[1],
+                         ((corner & 4) ? hi[2] : lo[2]) - t[2]};
+    for (int k = 0; k < 3; ++k) {
+      const double w = W[3 * k] * q[0] + W[3 * k + 1] * q[1] + W[3 * k + 2] * q[2];
+      if (!std::isfinite(w)) return false;
+      if (w < out.lo[k]) out.lo[k] = w;
+      if (w > out.hi[k]) out.hi[k] = w;
+    }
+  }
+  return true;
+}
 
 struct Encoder {
   const prt_scene_desc* s;
@@ -48,6 +95,48 @@ struct Encoder {
     ops[enter].b = (int)ops.size();  // skip target: first op after this node
     if (depth_in + 1 > max_depth) max_depth = depth_in + 1;
     return depth_in + 1;
+  }
+
+  // bounds of everything the reference's CSG evaluation of subtree t can report as a hit:
+  // INTERSECT -> overlap of the children, DIFFERENCE -> the left child, UNION -> hull
+  bool solid_box(int t, Box3& out) const {
+    const TreeNode& n = tree[t];
+    if (n.kind == PRT_LEAF) return leaf_world_box(s, n.leaf, out);
+    Box3 l, r;
+    if (!solid_box(n.l, l) || !solid_box(n.r, r)) return false;
+    if (n.kind == PRT_DIFFERENCE) {
+      out = l;
+    } else if (n.kind == PRT_INTERSECT) {
+      out.empty = l.empty || r.empty;
+      for (int k = 0; k < 3; ++k) {
+        out.lo[k] = l.lo[k] > r.lo[k] ? l.lo[k] : r.lo[k];
+        out.hi[k] = l.hi[k] < r.hi[k] ? l.hi[k] : r.hi[k];
+        if (out.lo[k] > out.hi[k]) out.empty = true;
+      }
+    } else {
+      if (l.empty) { out = r; return true; }
+      if (r.empty) { out = l; return true; }
+      out.empty = false;
+      for (int k = 0; k < 3; ++k) {
+        out.lo[k] = l.lo[k] < r.lo[k] ? l.lo[k] : r.lo[k];
+        out.hi[k] = l.hi[k] > r.hi[k] ? l.hi[k] : r.hi[k];
+      }
+    }
+    return true;
+  }
+
+  // true when the caller's bounding box of root node t contains solid_box(t) (to rounding):
+  // only then may the kernel prune the component by its box (prt_device.cuh eval_component)
+  bool root_box_is_bound(int t) const {
+    Box3 b;
+    if (tree[t].kind == PRT_LEAF || !solid_box(t, b)) return false;
+    if (b.empty) return true;
+    const double* a = s->node_aabb + 6 * tree[t].node;
+    for (int k = 0; k < 3; ++k) {
+      const double tol = 1e-12 * (1.0 + std::fabs(b.lo[k]) + std::fabs(b.hi[k]));
+      if (!(a[2 * k] <= b.lo[k] + tol) || !(a[2 * k + 1] >= b.hi[k] - tol)) return false;
+    }
+    return true;
   }
 };
 
@@ -100,6 +189,7 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
     if (comp_slots[c] > max_slots) max_slots = comp_slots[c];
     comp_begin[c] = (int)enc.ops.size();
     enc.emit(root, 0);
+    if (enc.tree[root].kind != PRT_LEAF && enc.root_box_is_bound(root)) enc.ops[comp_begin[c]].c |= 1;
   }
   comp_begin[d->n_components] = (int)enc.ops.size();
   if (enc.max_depth > prt::kMaxDepth) return fail(PRT_ERR_LIMIT, "CSG tree nests too deeply on the right");
@@ -122,6 +212,14 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   h.n_leaves = d->n_leaves;
   h.n_aabb = (int)enc.aabb.size() / 6;
   h.max_slots = max_slots;
+  {
+    bool tame = true;
+    for (double v : enc.aabb) {
+      const double av = std::fabs(v);
+      if (!(v == 0.0 || (av >= 0x1p-823 && av < 0x1p677))) tame = false;
+    }
+    h.flags = tame ? 1 : 0;
+  }
   auto align8 = [](int x) { return (x + 7) & ~7; };
   int off = align8((int)sizeof(prt::BlobHeader));
   h.off_comp = off;

@@ -30,8 +30,12 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
   return v;
 }
 
+#ifndef PRT_MIN_BLOCKS
+#define PRT_MIN_BLOCKS 3
+#endif
+
 template <bool RECORD>
-__global__ void __launch_bounds__(kTileRays) trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char s_blob[];
   __shared__ int s_wcount[kTileRays / 32];
   __shared__ long long s_base;
@@ -270,9 +274,11 @@ __global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned cha
   HitStack S;
   S.flags = 0;
   bool tie = false;
-  eval_component(sc, sc.comp[component], sc.comp[component + 1], p0, p1, p2, v0, v1, v2, S, tie);
+  const bool any =
+      eval_component(sc, sc.comp[component], sc.comp[component + 1], p0, p1, p2, v0, v1, v2,
+                     make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0), false, PRT_INF, S, tie);
   const int b = buf_of(S, 0);
-  const int len = S.len[0];
+  const int len = any ? S.len[0] : 0;
   for (int k = 0; k < slots; ++k) {
     hits[k * n + i] = (k < len) ? S.t[b][k] : PRT_INF;
     sids[k * n + i] = (k < len) ? (long long)sc.leaves[S.leaf[b][k]].sid : -1;

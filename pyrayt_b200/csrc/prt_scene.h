@@ -16,10 +16,14 @@ constexpr int kTileRays = 256;     // rays per tile == threads per block of the 
 constexpr int kMaxSlots = 32;      // PRT_MAX_SLOTS
 constexpr int kMaxDepth = 6;       // simultaneously live hit lists while evaluating one component
 constexpr int kFrameCols = 15;
+// slack (world units) of the exact component pruning: hit parameters and box parameters of the
+// same point differ by rounding only (~1e-13 at scene scale), the ray offset is 1e-6
+constexpr double kCullMargin = 1e-7;
 
 enum OpKind : int {
   OP_LEAF = 0,        // a = leaf              : push the leaf's hit pair
-  OP_ENTER = 1,       // a = aabb, b = skip op : world-space box test; on miss push an empty list and jump to b
+  OP_ENTER = 1,       // a = aabb, b = skip op, c = flags : world-space box test; on miss push an empty list and
+                      // jump to b.  c & 1 (root only): the box provably contains the solid -> pruning allowed
   OP_MERGE = 2,       // a = csg operation     : pop R, pop L, push array_csg(L, R)
   OP_MERGE_LEAF = 3   // a = csg operation, b = leaf : top := array_csg(top, leaf pair)  (right child is a leaf)
 };
@@ -46,7 +50,8 @@ struct BlobHeader {
   int off_leaves;  // Leaf[n_leaves]
   int total_bytes;
   int max_slots;   // largest component hit-list length
-  int pad[2];
+  int flags;       // bit 0: every bounding-box span is 0 or in [2^-823, 2^677) (fast slab test allowed)
+  int pad;
 };
 
 // arguments of the trace kernel (filled by prt_trace)

@@ -59,3 +59,12 @@ def intersect(scene, component, rays):
                                   sids.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
     assert rc == 0
     return hits, sids
+
+
+def prune_flags(scene):
+    """Per component: 1 = bounding-box pruning proven safe, 0 = disabled, -1 = bare leaf."""
+    flags = np.zeros(scene.n_components, dtype=np.int32)
+    desc = scene.as_desc()
+    rc = lib().prt_emul_prune_flags(ctypes.byref(desc), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert rc == 0
+    return flags

@@ -80,13 +80,32 @@ int prt_emul_intersect(const prt_scene_desc* d, int comp, const double* rays, lo
     prt::HitStack S;
     S.flags = 0;
     bool tie = false;
-    prt::eval_component(sc, sc.comp[comp], sc.comp[comp + 1], rays[0 * n + i], rays[1 * n + i], rays[2 * n + i],
-                        rays[4 * n + i], rays[5 * n + i], rays[6 * n + i], S, tie);
+    const bool any = prt::eval_component(
+        sc, sc.comp[comp], sc.comp[comp + 1], rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i],
+        rays[5 * n + i], rays[6 * n + i],
+        prt::make_ray_inv(rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i], rays[5 * n + i],
+                          rays[6 * n + i], (sc.h->flags & 1) != 0),
+        false, INFINITY, S, tie);
     const int b = prt::buf_of(S, 0);
+    const int len = any ? S.len[0] : 0;
     for (int k = 0; k < m; ++k) {
-      hits[k * n + i] = (k < S.len[0]) ? S.t[b][k] : INFINITY;
-      sids[k * n + i] = (k < S.len[0]) ? (long long)sc.leaves[S.leaf[b][k]].sid : -1;
+      hits[k * n + i] = (k < len) ? S.t[b][k] : INFINITY;
+      sids[k * n + i] = (k < len) ? (long long)sc.leaves[S.leaf[b][k]].sid : -1;
     }
+  }
+  return 0;
+}
+
+// per component: 1 when the encoder proved the root box bounds the solid (pruning enabled)
+int prt_emul_prune_flags(const prt_scene_desc* d, int* flags) {
+  std::vector<unsigned char> blob;
+  std::vector<int> slots;
+  std::string err;
+  if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
+  const prt::SceneView sc = prt::make_view(blob.data());
+  for (int c = 0; c < sc.h->n_components; ++c) {
+    const prt::Op first = sc.ops[sc.comp[c]];
+    flags[c] = (first.kind == prt::OP_ENTER) ? (first.c & 1) : -1;
   }
   return 0;
 }

@@ -56,6 +56,57 @@ def difference(a, b, aabb=BIG_BOX):
     return Node(NODE_DIFFERENCE, a, b, aabb)
 
 
+def leaf_box(o: Leaf):
+    """World-space AABB of a leaf the way the reference builds it (bounding cube corners -> world)."""
+    t, p = o.ptype, o.params
+    if t == SPHERE:
+        lo, hi = [-p[0]] * 3, [p[0]] * 3
+    elif t == PARABOLOID:
+        r = np.sqrt(4 * p[0] * p[1])
+        lo, hi = [-r, -r, 0], [r, r, p[1]]
+    elif t == PLANE:
+        lo, hi = [-p[0] / 2, -p[1] / 2, -0.01], [p[0] / 2, p[1] / 2, 0.01]
+    elif t == CUBE:
+        lo, hi = [p[0], p[2], p[4]], [p[1], p[3], p[5]]
+    else:
+        lo, hi = [-p[0], -p[0], p[1]], [p[0], p[0], p[2]]
+    corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]).T
+    w = o.world @ corners
+    return np.stack([w[:3].min(axis=1), w[:3].max(axis=1)], axis=1)  # (3, 2)
+
+
+def tight_box(o):
+    """Conservative box of a (sub)tree: INTERSECT overlap, DIFFERENCE left child, UNION hull."""
+    if isinstance(o, Leaf):
+        return leaf_box(o)
+    l, r = tight_box(o.left), tight_box(o.right)
+    if o.op == NODE_DIFFERENCE:
+        return l
+    if o.op == NODE_INTERSECT:
+        return np.stack([np.maximum(l[:, 0], r[:, 0]), np.minimum(l[:, 1], r[:, 1])], axis=1)
+    return np.stack([np.minimum(l[:, 0], r[:, 0]), np.maximum(l[:, 1], r[:, 1])], axis=1)
+
+
+def assign_boxes(o, rng):
+    """Give every CSG node a box: tight (pruning provable), huge, or deliberately too small."""
+    if isinstance(o, Leaf):
+        return
+    assign_boxes(o.left, rng)
+    assign_boxes(o.right, rng)
+    b = tight_box(o)
+    if np.any(b[:, 0] >= b[:, 1]):
+        o.aabb = BIG_BOX
+        return
+    mode = int(rng.integers(0, 4))
+    if mode == 0:
+        o.aabb = BIG_BOX
+    elif mode == 3:  # shrunk: the reference-style cull now hides parts of the solid; pruning must stay off
+        c, h = b.mean(axis=1), (b[:, 1] - b[:, 0]) / 2
+        o.aabb = tuple(np.stack([c - 0.6 * h, c + 0.6 * h], axis=1).reshape(6))
+    else:
+        o.aabb = tuple(b.reshape(6))
+
+
 def build(components) -> FlatScene:
     comp_begin, kind, nleaf, aabb = [0], [], [], []
     ltype, lobj, lprm, lns, lsid, lmat, lmatp = [], [], [], [], [], [], []
@@ -149,6 +200,8 @@ def random_scene_and_rays(seed, n_rays=512):
             comps.append(ops[int(rng.integers(0, 3))](ops[int(rng.integers(0, 3))](prim(kw), prim(kw)), prim(kw)))
         else:  # right-nested
             comps.append(ops[int(rng.integers(0, 3))](prim(kw), ops[int(rng.integers(0, 3))](prim(kw), prim(kw))))
+    for c in comps:
+        assign_boxes(c, rng)
     # enclose in absorbing walls so most rays end on something
     for ax in range(3):
         for sgn in (-1, 1):
