@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--zero-copy", action="store_true", help="e2e: gather kernel writes straight into pinned host memory")
     return ap.parse_args()
 
 
@@ -329,7 +330,8 @@ def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ra
 
     def step():
         dev_in.copy_(h_rays, non_blocking=True)
-        r = engine.trace(dev_in, generation_limit=G, record="all", to_host=True, host_frame=h_frame)
+        r = engine.trace(dev_in, generation_limit=G, record="all", to_host=True, host_frame=h_frame,
+                         zero_copy=args.zero_copy)
         assert r.rows == rows
         return r
 
