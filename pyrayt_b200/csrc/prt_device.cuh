@@ -19,6 +19,16 @@
 #endif
 
 namespace prt {
+PRT_HD int popc32(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+}  // namespace prt
+
+namespace prt {
 
 #define PRT_INF (__builtin_huge_val())
 
@@ -85,8 +95,9 @@ PRT_HD double div_fast(double a, const Rcp& R) {
 }
 
 PRT_HD double div_by(double a, const Rcp& R) {
-  if (!(exp_of(a) - kExpLo < R.lim)) return a / R.b;  // zero, tiny, huge, inf, NaN or an unsafe denominator
-  return div_fast(a, R);
+  if (exp_of(a) - kExpLo < R.lim) return div_fast(a, R);
+  if (a == 0.0 && R.lim != 0u) return a * R.r;  // signed zero, like a / b
+  return a / R.b;                               // tiny, huge, inf, NaN or an unsafe denominator
 }
 
 // per-generation reciprocals of a ray direction, shared by every bounding-box test against it
@@ -100,6 +111,7 @@ struct RayInv {
 struct SceneView {
   const BlobHeader* h;
   const int* comp;
+  const int* shape;
   const Op* ops;
   const double* aabb;
   const Leaf* leaves;
@@ -109,6 +121,7 @@ PRT_HD SceneView make_view(const unsigned char* blob) {
   SceneView s;
   s.h = reinterpret_cast<const BlobHeader*>(blob);
   s.comp = reinterpret_cast<const int*>(blob + s.h->off_comp);
+  s.shape = reinterpret_cast<const int*>(blob + s.h->off_shape);
   s.ops = reinterpret_cast<const Op*>(blob + s.h->off_ops);
   s.aabb = reinterpret_cast<const double*>(blob + s.h->off_aabb);
   s.leaves = reinterpret_cast<const Leaf*>(blob + s.h->off_leaves);
@@ -382,19 +395,19 @@ PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double&
       break;
   }
   if (!unit) {
-    const double nrm = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-    a0 /= nrm;
-    a1 /= nrm;
-    a2 /= nrm;
+    const Rcp nrm = make_rcp(sqrt(a0 * a0 + a1 * a1 + a2 * a2));
+    a0 = div_by(a0, nrm);
+    a1 = div_by(a1, nrm);
+    a2 = div_by(a2, nrm);
   }
   // M_obj^T n_obj, w dropped, normalise, flip (world_objects.py:411-418)
   double w0 = L.m[0] * a0 + L.m[4] * a1 + L.m[8] * a2;
   double w1 = L.m[1] * a0 + L.m[5] * a1 + L.m[9] * a2;
   double w2 = L.m[2] * a0 + L.m[6] * a1 + L.m[10] * a2;
-  const double wn = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
-  n0 = (w0 / wn) * L.nscale;
-  n1 = (w1 / wn) * L.nscale;
-  n2 = (w2 / wn) * L.nscale;
+  const Rcp wn = make_rcp(sqrt(w0 * w0 + w1 * w1 + w2 * w2));
+  n0 = div_by(w0, wn) * L.nscale;
+  n1 = div_by(w1, wn) * L.nscale;
+  n2 = div_by(w2, wn) * L.nscale;
 }
 
 // ---------------------------------------------------------------- CSG hit lists
@@ -514,6 +527,127 @@ PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, d
   return true;
 }
 
+// ---------------------------------------------------------------- register-only left-deep components
+//
+// Every reference factory builds a left-deep tree of two or three leaves ((A op1 B) op2 C,
+// SURVEY 8(a3)).  For those shapes the streaming merge is evaluated in closed form, entirely in
+// registers: in the stable merge of two sorted lists the position of an entry is its own index
+// plus the number of entries of the other list that precede it (strictly smaller for a left
+// entry, smaller-or-equal for a right entry: the left child wins ties), and array_csg's running
+// count at that position (csg.py:41-48) depends only on the parities of those two numbers.  The
+// result is the same keep/drop decision per entry as merge_lists makes, without lists in memory.
+
+// array_csg's keep rule for an entry whose running count is `cnt` after and `prev` before it
+PRT_HD bool csg_keep(int op, int cnt, int prev) {
+  return (op == PRT_UNION) ? ((cnt != 0) != (prev != 0)) : (cnt == 2 || prev == 2);
+}
+
+// merge of (a0,a1) [left] with (b0,b1) [right]; +inf marks a missing entry.  Outputs keep flags
+// and the merged positions of the four entries (A0, A1, B0, B1).
+PRT_HD void merge22(int op, double a0, double a1, double b0, double b1, bool keep[4], int pos[4], bool& tie) {
+  const bool va0 = a0 < PRT_INF, va1 = a1 < PRT_INF, vb0 = b0 < PRT_INF, vb1 = b1 < PRT_INF;
+  const bool l00 = b0 < a0, l01 = b0 < a1, l10 = b1 < a0, l11 = b1 < a1;  // l[j][i] = b_j < a_i
+  const int rb0 = (int)l00 + (int)l10, rb1 = (int)l01 + (int)l11;
+  const int lb0 = (int)(va0 && !l00) + (int)(va1 && !l01), lb1 = (int)(va0 && !l10) + (int)(va1 && !l11);
+  if ((va0 && vb0 && a0 == b0) || (va0 && vb1 && a0 == b1) || (va1 && vb0 && a1 == b0) || (va1 && vb1 && a1 == b1))
+    tie = true;
+  const int start = (op == PRT_DIFFERENCE) ? 1 : 0;
+  const int sR = (op == PRT_DIFFERENCE) ? -1 : 1;
+  int cnt;
+  cnt = start + 1 + sR * (rb0 & 1);                 // A0: first left entry (enters)
+  keep[0] = va0 && csg_keep(op, cnt, cnt - 1);
+  cnt = start + 0 + sR * (rb1 & 1);                 // A1: second left entry (exits)
+  keep[1] = va1 && csg_keep(op, cnt, cnt + 1);
+  cnt = start + (lb0 & 1) + sR;                     // B0
+  keep[2] = vb0 && csg_keep(op, cnt, cnt - sR);
+  cnt = start + (lb1 & 1);                          // B1
+  keep[3] = vb1 && csg_keep(op, cnt, cnt + sR);
+  pos[0] = rb0;
+  pos[1] = 1 + rb1;
+  pos[2] = lb0;
+  pos[3] = 1 + lb1;
+}
+
+// running best of one component: first positive kept entry in merged order
+PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
+  if (keep && t > 0 && t < ct) {
+    ct = t;
+    cl = leaf;
+  }
+}
+
+// shapes 2/3: [ENTER root][ENTER inner]? LEAF a, MERGE_LEAF(op1, b) [, MERGE_LEAF(op2, c)]
+PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0, double p1, double p2, double v0,
+                           double v1, double v2, const RayInv& inv, double best_t, double& ct, int& cl, bool& tie) {
+  ct = PRT_INF;
+  cl = -1;
+  const Op root = sc.ops[begin];
+  double b0, b1;
+  cube_hits(sc.aabb + 6 * root.a, p0, p1, p2, inv, b0, b1);
+  if (!(b0 < PRT_INF)) return;                                                      // csg.py:126-133
+  if ((root.c & 1) && (b1 < -kCullMargin || b0 > best_t + kCullMargin)) return;    // proven-box pruning
+  int pc = begin + 1;
+  bool inner_hit = true;
+  if (shape == 3) {
+    const Op inner = sc.ops[pc++];
+    cube_hits(sc.aabb + 6 * inner.a, p0, p1, p2, inv, b0, b1);
+    inner_hit = b0 < PRT_INF;
+  }
+  const Op oa = sc.ops[pc], ob = sc.ops[pc + 1];
+  double a0 = PRT_INF, a1 = PRT_INF, q0 = PRT_INF, q1 = PRT_INF;
+  bool keep[4] = {false, false, false, false};
+  int pos[4] = {0, 1, 2, 3};
+  if (inner_hit) {
+    leaf_hits(sc.leaves[oa.a], p0, p1, p2, v0, v1, v2, a0, a1);
+    leaf_hits(sc.leaves[ob.b], p0, p1, p2, v0, v1, v2, q0, q1);
+    merge22(ob.a, a0, a1, q0, q1, keep, pos, tie);
+  }
+  if (shape == 2) {
+    take_hit(keep[0], a0, oa.a, ct, cl);
+    take_hit(keep[1], a1, oa.a, ct, cl);
+    take_hit(keep[2], q0, ob.b, ct, cl);
+    take_hit(keep[3], q1, ob.b, ct, cl);
+    return;
+  }
+  // second merge: left = the kept entries of the first merge (index = number of kept entries before
+  // them in merged order), right = leaf c
+  const Op oc = sc.ops[pc + 2];
+  double c0, c1;
+  leaf_hits(sc.leaves[oc.b], p0, p1, p2, v0, v1, v2, c0, c1);
+  const int op2 = oc.a;
+  const double x[4] = {a0, a1, q0, q1};
+  unsigned km = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) km |= keep[e] ? (1u << pos[e]) : 0u;
+  const bool vc0 = c0 < PRT_INF, vc1 = c1 < PRT_INF;
+  const int start = (op2 == PRT_DIFFERENCE) ? 1 : 0;
+  const int sR = (op2 == PRT_DIFFERENCE) ? -1 : 1;
+  int lb0 = 0, lb1 = 0;
+  bool keep2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const bool l0 = c0 < x[e], l1 = c1 < x[e];
+    const int rb = (int)l0 + (int)l1;
+    lb0 += (int)(keep[e] && !l0);
+    lb1 += (int)(keep[e] && !l1);
+    if (keep[e] && ((vc0 && x[e] == c0) || (vc1 && x[e] == c1))) tie = true;
+    const int idx = popc32(km & ((1u << pos[e]) - 1u));
+    const int up = (idx & 1) ? -1 : 1;  // even index enters
+    const int cnt = start + ((idx + 1) & 1) + sR * (rb & 1);
+    keep2[e] = keep[e] && csg_keep(op2, cnt, cnt - up);
+  }
+  int cnt = start + (lb0 & 1) + sR;
+  const bool kc0 = vc0 && csg_keep(op2, cnt, cnt - sR);
+  cnt = start + (lb1 & 1);
+  const bool kc1 = vc1 && csg_keep(op2, cnt, cnt + sR);
+  take_hit(keep2[0], a0, oa.a, ct, cl);
+  take_hit(keep2[1], a1, oa.a, ct, cl);
+  take_hit(keep2[2], q0, ob.b, ct, cl);
+  take_hit(keep2[3], q1, ob.b, ct, cl);
+  take_hit(kc0, c0, oc.b, ct, cl);
+  take_hit(kc1, c1, oc.b, ct, cl);
+}
+
 // nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386)
 PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0,
                                             double v1, double v2, HitStack& S, double& best_t, int& best_leaf,
@@ -524,15 +658,26 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
   const int nc = sc.h->n_components;
   for (int c = 0; c < nc; ++c) {
     const int begin = sc.comp[c], end = sc.comp[c + 1];
-    const Op first = sc.ops[begin];
-    if (end - begin == 1 && first.kind == OP_LEAF) {
+    const int shape = sc.shape[c];
+    if (shape == SHAPE_LEAF) {
       // bare TracerSurface component: no list needed
+      const Op first = sc.ops[begin];
       double t0, t1;
       leaf_hits(sc.leaves[first.a], p0, p1, p2, v0, v1, v2, t0, t1);
       const double t = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
       if (t < best_t) {
         best_t = t;
         best_leaf = first.a;
+      }
+      continue;
+    }
+    if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
+      double ct;
+      int cl;
+      eval_left_deep(sc, begin, shape, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
+      if (ct < best_t) {  // strict: the earlier component wins ties (:384)
+        best_t = ct;
+        best_leaf = cl;
       }
       continue;
     }
@@ -596,6 +741,11 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   o.e1 = r.p1 + r.v1 * best_t;
   o.e2 = r.p2 + r.v2 * best_t;
   o.n_next = r.nidx;
+  // unit incoming direction: the row's tilt (:177) and refract()'s normalised vector (operations.py:125)
+  const Rcp rvn = make_rcp(vn);
+  o.t0n = div_by(r.v0, rvn);
+  o.t1n = div_by(r.v1, rvn);
+  o.t2n = div_by(r.v2, rvn);
   bool goes_on = true;
   if (L.mat == PRT_MAT_ABSORBER) {  // materials.py:47-50
     o.nv0 = 0;
@@ -615,19 +765,19 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
     // materials.py:70-75,:112-118,:136-145 ; operations.py:110-162
     double n0, n1, n2;
     world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
-    double n_mat;
-    if (L.mat == PRT_MAT_GLASS_CONST) {
-      n_mat = L.matp[0];
-    } else {
-      const double w2 = r.wl * r.wl;
-      n_mat = sqrt(1 + (L.matp[0] * w2) / (w2 - L.matp[3]) + (L.matp[1] * w2) / (w2 - L.matp[4]) +
-                   (L.matp[2] * w2) / (w2 - L.matp[5]));
-    }
-    const double u0 = r.v0 / vn, u1 = r.v1 / vn, u2 = r.v2 / vn;
+    const double u0 = o.t0n, u1 = o.t1n, u2 = o.t2n;
     const double cp = u0 * n0 + u1 * n1 + u2 * n2;
     const bool exiting = cp > 0;  // leaving the glass always enters n = 1 (operations.py:134)
-    const double n2l = exiting ? 1.0 : n_mat;
-    if (exiting) {
+    double n2l = 1.0;
+    if (!exiting) {  // index_at() only matters when entering
+      if (L.mat == PRT_MAT_GLASS_CONST) {
+        n2l = L.matp[0];
+      } else {
+        const double w2 = r.wl * r.wl;
+        n2l = sqrt(1 + (L.matp[0] * w2) / (w2 - L.matp[3]) + (L.matp[1] * w2) / (w2 - L.matp[4]) +
+                   (L.matp[2] * w2) / (w2 - L.matp[5]));
+      }
+    } else {
       n0 = -n0;
       n1 = -n1;
       n2 = -n2;
@@ -647,10 +797,10 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
       o.nv1 = u1 + k * n1;
       o.nv2 = u2 + k * n2;
     }
-    const double nn = sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2);
-    o.nv0 /= nn;
-    o.nv1 /= nn;
-    o.nv2 /= nn;
+    const Rcp nn = make_rcp(sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2));
+    o.nv0 = div_by(o.nv0, nn);
+    o.nv1 = div_by(o.nv1, nn);
+    o.nv2 = div_by(o.nv2, nn);
   } else {
     c.untr++;  // the reference raises AttributeError here
     return false;
@@ -658,9 +808,6 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   c.seg++;
   o.row = true;
   o.sid = L.sid;
-  o.t0n = r.v0 / vn;  // unit tilt of the incoming direction (:177)
-  o.t1n = r.v1 / vn;
-  o.t2n = r.v2 / vn;
   if (g + 1 == generation_limit) {
     c.lim++;
     return false;

@@ -156,6 +156,7 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   Encoder enc;
   enc.s = d;
   std::vector<int> comp_begin(d->n_components + 1, 0);
+  std::vector<int> comp_shape;
   comp_slots.assign(d->n_components, 0);
   int max_slots = 2;
   for (int c = 0; c < d->n_components; ++c) {
@@ -189,6 +190,18 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
     if (comp_slots[c] > max_slots) max_slots = comp_slots[c];
     comp_begin[c] = (int)enc.ops.size();
     enc.emit(root, 0);
+    {
+      const prt::Op* o = enc.ops.data() + comp_begin[c];
+      const int len = (int)enc.ops.size() - comp_begin[c];
+      int shape = prt::SHAPE_GENERIC;
+      if (len == 1 && o[0].kind == prt::OP_LEAF) shape = prt::SHAPE_LEAF;
+      else if (len == 3 && o[0].kind == prt::OP_ENTER && o[1].kind == prt::OP_LEAF && o[2].kind == prt::OP_MERGE_LEAF)
+        shape = prt::SHAPE_LEFT2;
+      else if (len == 5 && o[0].kind == prt::OP_ENTER && o[1].kind == prt::OP_ENTER && o[2].kind == prt::OP_LEAF &&
+               o[3].kind == prt::OP_MERGE_LEAF && o[4].kind == prt::OP_MERGE_LEAF)
+        shape = prt::SHAPE_LEFT3;
+      comp_shape.push_back(shape);
+    }
     if (enc.tree[root].kind != PRT_LEAF && enc.root_box_is_bound(root)) enc.ops[comp_begin[c]].c |= 1;
   }
   comp_begin[d->n_components] = (int)enc.ops.size();
@@ -224,6 +237,8 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   int off = align8((int)sizeof(prt::BlobHeader));
   h.off_comp = off;
   off = align8(off + (int)sizeof(int) * (d->n_components + 1));
+  h.off_shape = off;
+  off = align8(off + (int)sizeof(int) * (d->n_components > 0 ? d->n_components : 1));
   h.off_ops = off;
   off = align8(off + (int)sizeof(prt::Op) * h.n_ops);
   h.off_aabb = off;
@@ -234,6 +249,7 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   blob.assign((size_t)off, 0);
   std::memcpy(blob.data(), &h, sizeof h);
   std::memcpy(blob.data() + h.off_comp, comp_begin.data(), sizeof(int) * comp_begin.size());
+  if (!comp_shape.empty()) std::memcpy(blob.data() + h.off_shape, comp_shape.data(), sizeof(int) * comp_shape.size());
   if (h.n_ops) std::memcpy(blob.data() + h.off_ops, enc.ops.data(), sizeof(prt::Op) * enc.ops.size());
   if (h.n_aabb) std::memcpy(blob.data() + h.off_aabb, enc.aabb.data(), sizeof(double) * enc.aabb.size());
   prt::Leaf* leaves = reinterpret_cast<prt::Leaf*>(blob.data() + h.off_leaves);

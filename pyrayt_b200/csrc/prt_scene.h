@@ -28,6 +28,14 @@ enum OpKind : int {
   OP_MERGE_LEAF = 3   // a = csg operation, b = leaf : top := array_csg(top, leaf pair)  (right child is a leaf)
 };
 
+// evaluation strategy of a component, chosen by the encoder
+enum Shape : int {
+  SHAPE_GENERIC = 0,  // any tree: preorder interpreter with hit lists in local memory
+  SHAPE_LEAF = 1,     // bare TracerSurface
+  SHAPE_LEFT2 = 2,    // ENTER, LEAF a, MERGE_LEAF b                     (A op B)
+  SHAPE_LEFT3 = 3     // ENTER, ENTER, LEAF a, MERGE_LEAF b, MERGE_LEAF c  ((A op1 B) op2 C)
+};
+
 struct Op {
   int kind, a, b, c;
 };
@@ -51,7 +59,7 @@ struct BlobHeader {
   int total_bytes;
   int max_slots;   // largest component hit-list length
   int flags;       // bit 0: every bounding-box span is 0 or in [2^-823, 2^677) (fast slab test allowed)
-  int pad;
+  int off_shape;   // int[n_components] : Shape per component
 };
 
 // arguments of the trace kernel (filled by prt_trace)

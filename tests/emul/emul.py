@@ -68,3 +68,12 @@ def prune_flags(scene):
     rc = lib().prt_emul_prune_flags(ctypes.byref(desc), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
     assert rc == 0
     return flags
+
+
+def selfcheck_left_deep():
+    """(disagreements, cases) of the closed-form left-deep evaluation vs the streaming merge."""
+    cases = ctypes.c_longlong()
+    L = lib()
+    L.prt_emul_selfcheck_left_deep.restype = ctypes.c_longlong
+    bad = L.prt_emul_selfcheck_left_deep(ctypes.byref(cases))
+    return int(bad), int(cases.value)

@@ -46,3 +46,9 @@ def test_component_intersect_equals_oracle(seed):
         fin = np.isfinite(oh)
         assert np.array_equal(esid[fin], osid[fin])
         assert np.all(esid[np.isposinf(eh)] == -1)
+
+
+def test_closed_form_left_deep_merge_equals_streaming_merge():
+    """All sorted pairs over {-inf,-2,-1,1,2,3,+inf} for A, B, C and all 9 operation pairs."""
+    bad, cases = emul.selfcheck_left_deep()
+    assert cases == 9 * 28 ** 3 and bad == 0
