@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define PRT_HD __host__ __device__ __forceinline__
+#define PRT_HD_CALL __host__ __device__ __noinline__  // one copy in the kernel: keeps the hot loop inside the I-cache
 #else
 #define PRT_HD inline
+#define PRT_HD_CALL inline
 #endif
 
 namespace prt {
@@ -102,10 +104,10 @@ PRT_HD double div_by(double a, const Rcp& R) {
 
 // per-generation reciprocals of a ray direction, shared by every bounding-box test against it
 struct RayInv {
-  Rcp r0, r1, r2;
-  bool z0, z1, z2;
-  bool fast;       // guard-free slab arithmetic is provably exact for this ray (see cube_hits)
-  int s0, s1, s2;  // per axis: 0 if the ray runs towards +axis (near face = lo) else 1
+  double r0, r1, r2;  // RN(1 / (d_k + z_k))
+  unsigned bits;      // 0-2: z_k (|d_k| <= 1e-8), 3-5: s_k (1 if the ray runs towards -axis: near face = hi),
+                      // 6: fast (guard-free slab arithmetic is provably exact for this ray, see cube_hits),
+                      // 7-9: reciprocal k usable by div_by (denominator in the safe exponent window)
 };
 
 struct SceneView {
@@ -174,44 +176,56 @@ PRT_HD bool tame(double x) { return x == 0.0 || (exp_of(x) - 200u < 1700u - 200u
 // ray will be tested against has spans that are 0 or in [2^-823, 2^677) (BlobHeader.flags & 1)
 PRT_HD RayInv make_ray_inv(double o0, double o1, double o2, double d0, double d1, double d2, bool boxes_tame) {
   RayInv I;
-  I.z0 = isz(d0);
-  I.z1 = isz(d1);
-  I.z2 = isz(d2);
-  const double e0 = d0 + (I.z0 ? 1.0 : 0.0), e1 = d1 + (I.z1 ? 1.0 : 0.0), e2 = d2 + (I.z2 ? 1.0 : 0.0);
-  I.r0 = make_rcp(e0);
-  I.r1 = make_rcp(e1);
-  I.r2 = make_rcp(e2);
-  I.s0 = e0 < 0 ? 1 : 0;
-  I.s1 = e1 < 0 ? 1 : 0;
-  I.s2 = e2 < 0 ? 1 : 0;
+  const bool z0 = isz(d0), z1 = isz(d1), z2 = isz(d2);
+  const double e0 = d0 + (z0 ? 1.0 : 0.0), e1 = d1 + (z1 ? 1.0 : 0.0), e2 = d2 + (z2 ? 1.0 : 0.0);
+  const Rcp R0 = make_rcp(e0), R1 = make_rcp(e1), R2 = make_rcp(e2);
+  I.r0 = R0.r;
+  I.r1 = R1.r;
+  I.r2 = R2.r;
   // Fast slab form: differences of tame numbers are 0 or >= 2^-876 and < 2^678, denominators are in
   // [2^-66, 2^66) -> every quotient and its FMA residual stay normal, so div_fast is exact.
   const bool den_ok = (exp_of(e0) - 957u < 132u) && (exp_of(e1) - 957u < 132u) && (exp_of(e2) - 957u < 132u);
-  I.fast = boxes_tame && !I.z0 && !I.z1 && !I.z2 && den_ok && tame(o0) && tame(o1) && tame(o2);
+  const bool fast = boxes_tame && !z0 && !z1 && !z2 && den_ok && tame(o0) && tame(o1) && tame(o2);
+  I.bits = (z0 ? 1u : 0u) | (z1 ? 2u : 0u) | (z2 ? 4u : 0u) | (e0 < 0 ? 8u : 0u) | (e1 < 0 ? 16u : 0u) |
+           (e2 < 0 ? 32u : 0u) | (fast ? 64u : 0u) | (R0.lim ? 128u : 0u) | (R1.lim ? 256u : 0u) |
+           (R2.lim ? 512u : 0u);
   return I;
 }
 
-// Cube.intersect (primitives.py:516-581); also every CSG node's world-space AABB (csg.py:126-128)
-PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, const RayInv& I, double& t0,
-                      double& t1) {
+// the literal three-slab form (parallel rays, guarded divisions): rare, kept out of line
+PRT_HD void cube_hits_generic(const double* sp, double o0, double o1, double o2, double d0, double d1, double d2,
+                                   const RayInv& I, double& lo, double& hi) {
+  const bool z0 = I.bits & 1u, z1 = I.bits & 2u, z2 = I.bits & 4u;
+  const Rcp R0 = {d0 + (z0 ? 1.0 : 0.0), I.r0, (I.bits & 128u) ? kExpSpan : 0u};
+  const Rcp R1 = {d1 + (z1 ? 1.0 : 0.0), I.r1, (I.bits & 256u) ? kExpSpan : 0u};
+  const Rcp R2 = {d2 + (z2 ? 1.0 : 0.0), I.r2, (I.bits & 512u) ? kExpSpan : 0u};
+  double mn0, mx0, mn1, mx1, mn2, mx2;
+  cube_axis(o0, z0, R0, sp[0], sp[1], mn0, mx0);
+  cube_axis(o1, z1, R1, sp[2], sp[3], mn1, mx1);
+  cube_axis(o2, z2, R2, sp[4], sp[5], mn2, mx2);
+  lo = fmax(fmax(mn0, mn1), mn2);
+  hi = fmin(fmin(mx0, mx1), mx2);
+}
+
+// Cube.intersect (primitives.py:516-581); also every CSG node's world-space AABB (csg.py:126-128).
+// (d0,d1,d2) is the direction the reciprocals in I were made from.
+PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, double d0, double d1, double d2,
+                      const RayInv& I, double& t0, double& t1) {
   double lo, hi;
-  if (I.fast) {
+  if (I.bits & 64u) {
     // the sign of the direction says which face is the near one: no sort, no parallel-ray cases;
     // values are bit-identical to the generic path (rounding is monotonic)
-    const double mn0 = div_fast(-(o0 - sp[I.s0]), I.r0), mx0 = div_fast(-(o0 - sp[1 - I.s0]), I.r0);
-    const double mn1 = div_fast(-(o1 - sp[2 + I.s1]), I.r1), mx1 = div_fast(-(o1 - sp[3 - I.s1]), I.r1);
-    const double mn2 = div_fast(-(o2 - sp[4 + I.s2]), I.r2), mx2 = div_fast(-(o2 - sp[5 - I.s2]), I.r2);
+    const int s0 = (I.bits >> 3) & 1, s1 = (I.bits >> 4) & 1, s2 = (I.bits >> 5) & 1;
+    const Rcp R0 = {d0, I.r0, 1u}, R1 = {d1, I.r1, 1u}, R2 = {d2, I.r2, 1u};
+    const double mn0 = div_fast(-(o0 - sp[s0]), R0), mx0 = div_fast(-(o0 - sp[1 - s0]), R0);
+    const double mn1 = div_fast(-(o1 - sp[2 + s1]), R1), mx1 = div_fast(-(o1 - sp[3 - s1]), R1);
+    const double mn2 = div_fast(-(o2 - sp[4 + s2]), R2), mx2 = div_fast(-(o2 - sp[5 - s2]), R2);
     lo = mn0 > mn1 ? mn0 : mn1;
     lo = lo > mn2 ? lo : mn2;
     hi = mx0 < mx1 ? mx0 : mx1;
     hi = hi < mx2 ? hi : mx2;
   } else {
-    double mn0, mx0, mn1, mx1, mn2, mx2;
-    cube_axis(o0, I.z0, I.r0, sp[0], sp[1], mn0, mx0);
-    cube_axis(o1, I.z1, I.r1, sp[2], sp[3], mn1, mx1);
-    cube_axis(o2, I.z2, I.r2, sp[4], sp[5], mn2, mx2);
-    lo = fmax(fmax(mn0, mn1), mn2);
-    hi = fmin(fmin(mx0, mx1), mx2);
+    cube_hits_generic(sp, o0, o1, o2, d0, d1, d2, I, lo, hi);
   }
   if (lo < hi) {
     t0 = lo;
@@ -328,7 +342,7 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       t1 = t;
     } break;
     case PRT_CUBE:  // primitives.py:516-581
-      cube_hits(L.prm, o0, o1, o2, make_ray_inv(o0, o1, o2, d0, d1, d2, false), t0, t1);
+      cube_hits(L.prm, o0, o1, o2, d0, d1, d2, make_ray_inv(o0, o1, o2, d0, d1, d2, false), t0, t1);
       break;
     default:
       t0 = PRT_INF;
@@ -489,7 +503,7 @@ PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, d
     const Op op = sc.ops[pc];
     if (op.kind == OP_ENTER) {
       double b0, b1;
-      cube_hits(sc.aabb + 6 * op.a, p0, p1, p2, inv, b0, b1);
+      cube_hits(sc.aabb + 6 * op.a, p0, p1, p2, v0, v1, v2, inv, b0, b1);
       if (!(b0 < PRT_INF)) {  // cube_hits returns finite values or (+inf,+inf): csg.py:126-128
         if (pc == begin) return false;  // root culled: no hits at all
         S.len[sp++] = 0;
@@ -583,14 +597,14 @@ PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0,
   cl = -1;
   const Op root = sc.ops[begin];
   double b0, b1;
-  cube_hits(sc.aabb + 6 * root.a, p0, p1, p2, inv, b0, b1);
+  cube_hits(sc.aabb + 6 * root.a, p0, p1, p2, v0, v1, v2, inv, b0, b1);
   if (!(b0 < PRT_INF)) return;                                                      // csg.py:126-133
   if ((root.c & 1) && (b1 < -kCullMargin || b0 > best_t + kCullMargin)) return;    // proven-box pruning
   int pc = begin + 1;
   bool inner_hit = true;
   if (shape == 3) {
     const Op inner = sc.ops[pc++];
-    cube_hits(sc.aabb + 6 * inner.a, p0, p1, p2, inv, b0, b1);
+    cube_hits(sc.aabb + 6 * inner.a, p0, p1, p2, v0, v1, v2, inv, b0, b1);
     inner_hit = b0 < PRT_INF;
   }
   const Op oa = sc.ops[pc], ob = sc.ops[pc + 1];

@@ -31,7 +31,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 #ifndef PRT_MIN_BLOCKS
-#define PRT_MIN_BLOCKS 3
+#define PRT_MIN_BLOCKS 2
 #endif
 
 template <bool RECORD>

@@ -12,7 +12,10 @@
 
 namespace prt {
 
-constexpr int kTileRays = 256;     // rays per tile == threads per block of the trace kernel
+#ifndef PRT_TILE
+#define PRT_TILE 256
+#endif
+constexpr int kTileRays = PRT_TILE;  // rays per tile == threads per block of the trace kernel
 constexpr int kMaxSlots = 32;      // PRT_MAX_SLOTS
 constexpr int kMaxDepth = 6;       // simultaneously live hit lists while evaluating one component
 constexpr int kFrameCols = 15;
