@@ -42,5 +42,5 @@ WORKLOADS = {
     "config4": Workload("config4", "config4_stack.scene.json", CONFIG4_SOURCE, 1 << 24, 64,
                         "synthetic 10-element spherical-lens CSG stack with 2 stops + detector (35 leaves), 2^24 rays"),
     "config5": Workload("config5", "config5_cavity.scene.json", CONFIG5_SOURCE, 1 << 25, 32,
-                        "paraboloid + TIR light pipe + cuboid-mirror cavity, 2^25 rays per GPU"),
+                        "parabolic mirror + BK7 TIR light pipe + two cuboid mirrors + detector (6 leaves), 2^25 rays per GPU"),
 }

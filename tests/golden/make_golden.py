@@ -121,18 +121,23 @@ def config4_stack():
 
 
 def config5_scene():
-    """Multi-bounce paraboloid / cuboid-mirror / TIR light-pipe scene.
+    """Multi-bounce paraboloid / TIR light-pipe / cuboid-mirror scene.
 
-    A point source at the focus of a parabolic mirror sends a collimated beam down +x into
-    a BK7 light pipe tilted 20 degrees (entering rays are trapped by total internal
-    reflection), then into a slightly tilted cavity of two cuboid mirrors in front of a
-    detector baffle.
+    A point source at the focus of ``parabolic_mirror(50, 5, aperture=40)`` (focus at the origin)
+    emits towards -x; the dish returns a collimated beam along +x.  ``m1`` (cuboid mirror, tilted
+    0.3 deg) sends it back to the dish, which focuses it through the origin into the end face of a
+    BK7 ``Cuboid.from_sides(200, 10, 10)`` light pipe whose axis is tilted 20 deg to the beam: rays
+    zig-zag down the pipe by total internal reflection (about 9 glass interactions per ray), leave
+    through the far face, and a second cuboid mirror ``m2`` folds them onto the detector baffle.
+    Part of the outgoing beam also crosses the pipe sideways (two refractions).  Measured with the
+    reference: 12.4 rows per ray on average, 51 % of the rays end on the detector.
     """
+    c20, s20 = np.cos(np.radians(20.0)), np.sin(np.radians(20.0))
     parab = pc.parabolic_mirror(50, 5, aperture=40)
-    pipe = cg.Cuboid.from_sides(200, 10, 10, material=matl.glass["BK7"]).rotate_z(20).move(130, 20, 0)
-    m1 = pc.plane_mirror(2, aperture=(60, 60)).rotate_z(2).move(300, 0, 0)
-    m2 = pc.plane_mirror(2, aperture=(60, 60)).rotate_z(-1.5).move(60, -70, 0)
-    det = pc.baffle((80, 80)).move(320, -60, 0)
+    pipe = cg.Cuboid.from_sides(200, 10, 10, material=matl.glass["BK7"]).rotate_z(20).move(106 * c20, 106 * s20, 0)
+    m1 = pc.plane_mirror(2, aperture=(60, 60)).rotate_z(0.3).move(120, 0, 0)
+    m2 = pc.plane_mirror(2, aperture=(60, 60)).rotate_z(-35).move(241 * c20, 241 * s20, 0)
+    det = pc.baffle((80, 80)).rotate_z(90).move(226, 160, 0)
     return [parab, pipe, m1, m2, det]
 
 
