@@ -96,10 +96,14 @@ PRT_HD double div_fast(double a, const Rcp& R) {
   return fma(e, R.r, q);
 }
 
+// the rare operands div_by cannot handle in 3 instructions: one shared out-of-line IEEE division
+// (inlining it at ~75 call sites made a quarter of the kernel's code)
+PRT_HD_CALL double slow_div(double a, double b) { return a / b; }
+
 PRT_HD double div_by(double a, const Rcp& R) {
   if (exp_of(a) - kExpLo < R.lim) return div_fast(a, R);
   if (a == 0.0 && R.lim != 0u) return a * R.r;  // signed zero, like a / b
-  return a / R.b;                               // tiny, huge, inf, NaN or an unsafe denominator
+  return slow_div(a, R.b);                      // tiny, huge, inf, NaN or an unsafe denominator
 }
 
 // per-generation reciprocals of a ray direction, shared by every bounding-box test against it
@@ -608,14 +612,29 @@ PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0,
     inner_hit = b0 < PRT_INF;
   }
   const Op oa = sc.ops[pc], ob = sc.ops[pc + 1];
-  double a0 = PRT_INF, a1 = PRT_INF, q0 = PRT_INF, q1 = PRT_INF;
+  const int lc = (shape == 3) ? sc.ops[pc + 2].b : -1;
+  const int op2 = (shape == 3) ? sc.ops[pc + 2].a : 0;
+  double a0 = PRT_INF, a1 = PRT_INF, q0 = PRT_INF, q1 = PRT_INF, c0 = PRT_INF, c1 = PRT_INF;
+  // one (not unrolled) loop over the leaves keeps a single copy of leaf_hits in the hot loop
+#pragma unroll 1
+  for (int k = inner_hit ? 0 : 2; k < shape; ++k) {
+    const int lf = (k == 0) ? oa.a : ((k == 1) ? ob.b : lc);
+    double t0, t1;
+    leaf_hits(sc.leaves[lf], p0, p1, p2, v0, v1, v2, t0, t1);
+    if (k == 0) {
+      a0 = t0;
+      a1 = t1;
+    } else if (k == 1) {
+      q0 = t0;
+      q1 = t1;
+    } else {
+      c0 = t0;
+      c1 = t1;
+    }
+  }
   bool keep[4] = {false, false, false, false};
   int pos[4] = {0, 1, 2, 3};
-  if (inner_hit) {
-    leaf_hits(sc.leaves[oa.a], p0, p1, p2, v0, v1, v2, a0, a1);
-    leaf_hits(sc.leaves[ob.b], p0, p1, p2, v0, v1, v2, q0, q1);
-    merge22(ob.a, a0, a1, q0, q1, keep, pos, tie);
-  }
+  if (inner_hit) merge22(ob.a, a0, a1, q0, q1, keep, pos, tie);
   if (shape == 2) {
     take_hit(keep[0], a0, oa.a, ct, cl);
     take_hit(keep[1], a1, oa.a, ct, cl);
@@ -625,10 +644,6 @@ PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0,
   }
   // second merge: left = the kept entries of the first merge (index = number of kept entries before
   // them in merged order), right = leaf c
-  const Op oc = sc.ops[pc + 2];
-  double c0, c1;
-  leaf_hits(sc.leaves[oc.b], p0, p1, p2, v0, v1, v2, c0, c1);
-  const int op2 = oc.a;
   const double x[4] = {a0, a1, q0, q1};
   unsigned km = 0;
 #pragma unroll
@@ -658,8 +673,8 @@ PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0,
   take_hit(keep2[1], a1, oa.a, ct, cl);
   take_hit(keep2[2], q0, ob.b, ct, cl);
   take_hit(keep2[3], q1, ob.b, ct, cl);
-  take_hit(kc0, c0, oc.b, ct, cl);
-  take_hit(kc1, c1, oc.b, ct, cl);
+  take_hit(kc0, c0, lc, ct, cl);
+  take_hit(kc1, c1, lc, ct, cl);
 }
 
 // nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386)
