@@ -208,10 +208,32 @@ int prt_gather_frame(const prt_records* records, int32_t generation_limit, const
 int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int64_t n,
                   double* d_hits, int64_t* d_sids, int32_t* slots_out, void* cuda_stream);
 
+/*
+ * Nearest positive hit over all components = RayTracer._st_propagate alone (pyrayt/_pyrayt.py:370-392);
+ * the same loop the reference's renderers run per pixel (tinygfx/g3d/renderers.py:72-94,:188-210).
+ * d_rays (2,4,N) as for prt_intersect.  d_t[i] = distance or +inf, d_sid[i] = surface id or -1;
+ * d_normals (optional, may be NULL): (3,N) world normal at the hit (get_world_normals,
+ * world_objects.py:401-418), NaN for a miss.
+ */
+int prt_nearest_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d_t, int64_t* d_sid,
+                    double* d_normals, void* cuda_stream);
+
+/*
+ * Re-encode a scene into an existing handle (same device buffer when the encoded size is unchanged):
+ * for optimisation loops that move components or change radii between thousands of small traces
+ * (examples/lens_design.ipynb cells 28-33).  The copy is enqueued on cuda_stream.
+ */
+int prt_scene_update(prt_scene* scene, const prt_scene_desc* host_scene, void* cuda_stream);
+
 /* seeded synthetic sources of SURVEY.md 8(d); see pyrayt_b200/sources.py for the exact law */
 typedef struct prt_source_desc {
   int32_t kind;        /* 1 = disk/field/wavelength fan (config 4), 2 = solid-angle cone (config 2),
-                          3 = Lambertian cone (config 5)                                              */
+                          3 = Lambertian cone (config 5);
+                          the reference's deterministic sources (pyrayt/components.py:511-613):
+                          10 = LineOfRays, 11 = CircleOfRays, 12 = ConeOfRays, 13 = WedgeOfRays with
+                          p[0] = spacing | diameter | cone angle [rad] | wedge angle [rad], p[1] = wavelength,
+                          p[2] = ray count of the source (== n_rays), p[3] = id of its first ray,
+                          p[4..15] = rows 0..2 of the source's 4x4 world matrix (first_index unused)      */
   int32_t reserved;
   uint64_t seed;
   double origin[3];

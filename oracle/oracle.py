@@ -158,3 +158,20 @@ def world_normal(scene, leaf: int, point):
     out = np.empty(3)
     lib().prt_oracle_world_normal(ctypes.byref(desc), leaf, _p(q), _p(out))
     return out
+
+
+def nearest(scene, rays: np.ndarray):
+    """_st_propagate alone: rays (2,4,N) -> (distance (N,), surface id (N,), world normals (3,N))."""
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(8, -1)
+    n = rays.shape[1]
+    t = np.empty(n)
+    sid = np.empty(n, dtype=np.int64)
+    nrm = np.empty((3, n))
+    desc = scene.as_desc()
+    L = lib()
+    L.prt_oracle_nearest.restype = ctypes.c_int
+    rc = L.prt_oracle_nearest(ctypes.byref(desc), _p(rays), ctypes.c_int64(n), _p(t),
+                              sid.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _p(nrm))
+    if rc:
+        raise RuntimeError("oracle nearest failed")
+    return t, sid, nrm

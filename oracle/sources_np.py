@@ -85,3 +85,43 @@ def generate(kind: int, seed: int, origin, p, n: int, first_index: int = 0) -> n
 def from_source(src, n: int, first_index: int = 0) -> np.ndarray:
     """Same rays as ``pyrayt_b200.sources.SyntheticSource.generate`` (host array)."""
     return generate(src.kind, src.seed, tuple(src.origin), list(src.p), n, first_index)
+
+
+def reference_source(kind: int, p, n: int) -> np.ndarray:
+    """NumPy restatement of pyrayt.components Line/Circle/Cone/WedgeOfRays.generate_rays
+    (pyrayt/components.py:481-613) for the descriptor layout of pyrayt_b200.sources.from_reference:
+    the same NumPy expressions as the reference, so it is bit-identical to it."""
+    rays = np.zeros((2, 4, n))
+    rays[0, 3] = 1
+    if kind == 10:
+        if n > 1:
+            rays[0, 1] = np.linspace(-p[0] / 2, p[0] / 2, n)
+        rays[1, 0] = 1
+    elif kind == 11:
+        theta = np.linspace(0, 2 * np.pi, n)
+        rays[0, 1] = p[0] / 2 * np.sin(theta)
+        rays[0, 2] = p[0] / 2 * np.cos(theta)
+        rays[1, 0] = 1
+    elif kind == 12:
+        if n > 1:
+            angles = 2 * np.pi * np.arange(0, n) / n
+            rays[1, 1] = np.sin(p[0]) * np.sin(angles)
+            rays[1, 2] = np.sin(p[0]) * np.cos(angles)
+        rays[1, 0] = np.cos(p[0])
+    elif kind == 13:
+        angles = np.linspace(-p[0] / 2, p[0] / 2, n)
+        rays[1, 0] = np.cos(angles)
+        rays[1, 1] = np.sin(angles)
+    else:
+        raise ValueError(kind)
+    M = np.eye(4)
+    M[:3] = np.asarray(p[4:16]).reshape(3, 4)
+    rays = np.matmul(M, rays)
+    rays[1] /= np.linalg.norm(rays[1], axis=0)
+    out = np.zeros((13, n))
+    out[:8] = rays.reshape(8, n)
+    out[9] = 100.0
+    out[10] = p[1]
+    out[11] = 1.0
+    out[12] = p[3] + np.arange(n)
+    return out

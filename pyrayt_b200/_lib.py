@@ -32,7 +32,7 @@ COUNTER_WORDS = 16
 EXPORTS = (
     "prt_abi_version", "prt_last_error", "prt_tile_rays", "prt_scene_create", "prt_scene_destroy",
     "prt_scene_n_leaves", "prt_trace", "prt_scan_runs", "prt_gather_frame", "prt_intersect",
-    "prt_generate_source", "prt_fp64_probe",
+    "prt_generate_source", "prt_fp64_probe", "prt_nearest_hit", "prt_scene_update",
 )
 
 
@@ -106,6 +106,10 @@ def load():
     lib.prt_intersect.argtypes = [vp, i32, vp, i64, vp, vp, ctypes.POINTER(i32), vp]
     lib.prt_generate_source.restype = ctypes.c_int
     lib.prt_generate_source.argtypes = [ctypes.POINTER(PrtSourceDesc), vp, i64, i64, i64, vp]
+    lib.prt_nearest_hit.restype = ctypes.c_int
+    lib.prt_nearest_hit.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.prt_scene_update.restype = ctypes.c_int
+    lib.prt_scene_update.argtypes = [vp, vp, vp]
     lib.prt_fp64_probe.restype = ctypes.c_int
     lib.prt_fp64_probe.argtypes = [vp, i32, i32, vp]
     if lib.prt_abi_version() != ABI_VERSION:

@@ -26,6 +26,8 @@ cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int 
 cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
                               long long first, cudaStream_t st);
 cudaError_t prt_launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);
+cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const double* rays, long long n, double* t_out,
+                               long long* sid_out, double* normals, cudaStream_t st);
 }
 
 struct prt_scene {
@@ -35,6 +37,7 @@ struct prt_scene {
   int n_leaves = 0;
   int n_components = 0;
   std::vector<int> comp_slots;
+  std::vector<unsigned char> staging;  // host copy of the last prt_scene_update (pageable -> the copy is synchronous enough)
 };
 
 namespace {
@@ -91,6 +94,36 @@ int prt_scene_create(const prt_scene_desc* d, int device, prt_scene** out) {
     return cuda_fail(e, "cudaMemcpy(scene)");
   }
   *out = sc;
+  return PRT_OK;
+}
+
+int prt_scene_update(prt_scene* sc, const prt_scene_desc* d, void* cuda_stream) {
+  if (!sc || !d) return fail(PRT_ERR_INVALID, "null argument");
+  std::vector<unsigned char> blob;
+  std::vector<int> comp_slots;
+  {
+    std::string err;
+    const int rc = prt::encode_scene(d, blob, comp_slots, err);
+    if (rc != PRT_OK) return fail(rc, err);
+  }
+  cudaError_t e = cudaSetDevice(sc->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if ((int)blob.size() != sc->blob_bytes) {  // topology changed: new device buffer
+    unsigned char* fresh = nullptr;
+    e = cudaMalloc(&fresh, blob.size());
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scene)");
+    cudaStreamSynchronize((cudaStream_t)cuda_stream);  // kernels still reading the old blob
+    cudaFree(sc->d_blob);
+    sc->d_blob = fresh;
+    sc->blob_bytes = (int)blob.size();
+  }
+  sc->staging = blob;  // keeps the host copy alive until the async copy has run
+  e = cudaMemcpyAsync(sc->d_blob, sc->staging.data(), sc->staging.size(), cudaMemcpyHostToDevice,
+                      (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scene)");
+  sc->n_leaves = d->n_leaves;
+  sc->n_components = d->n_components;
+  sc->comp_slots = comp_slots;
   return PRT_OK;
 }
 
@@ -181,10 +214,25 @@ int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int
   return PRT_OK;
 }
 
+int prt_nearest_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d_t, int64_t* d_sid, double* d_normals,
+                    void* cuda_stream) {
+  if (!scene) return fail(PRT_ERR_INVALID, "null scene");
+  if (n < 0) return fail(PRT_ERR_INVALID, "negative ray count");
+  if (n == 0) return PRT_OK;
+  if (!d_rays || !d_t || !d_sid) return fail(PRT_ERR_INVALID, "null buffer");
+  cudaError_t e = prt_launch_nearest(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
+                                     reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "nearest kernel launch");
+  return PRT_OK;
+}
+
 int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_rays, int64_t ray_stride,
                         int64_t first_index, void* cuda_stream) {
   if (!src || (!d_rays && n_rays > 0)) return fail(PRT_ERR_INVALID, "null argument");
-  if (src->kind < 1 || src->kind > 3) return fail(PRT_ERR_INVALID, "unknown source kind");
+  const bool synthetic = src->kind >= 1 && src->kind <= 3;
+  const bool reference = src->kind >= 10 && src->kind <= 13;
+  if (!synthetic && !reference) return fail(PRT_ERR_INVALID, "unknown source kind");
+  if (reference && (double)n_rays != src->p[2]) return fail(PRT_ERR_INVALID, "n_rays must equal the source's ray count p[2]");
   if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
   cudaError_t e = prt_launch_source(src, d_rays, n_rays, ray_stride, first_index, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "source kernel launch");

@@ -285,6 +285,41 @@ __global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned cha
   }
 }
 
+// ---------------------------------------------------------------- _st_propagate alone (renderers, probes)
+
+__global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) nearest_kernel(const unsigned char* blob, int blob_bytes,
+                                                                           const double* rays, long long n, double* t_out,
+                                                                           long long* sid_out, double* normals) {
+  extern __shared__ __align__(16) unsigned char s_blob[];
+  {
+    const int words = blob_bytes / 8;
+    const double* src = reinterpret_cast<const double*>(blob);
+    double* dst = reinterpret_cast<double*>(s_blob);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const SceneView sc = make_view(s_blob);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
+  const double v0 = rays[4 * n + i], v1 = rays[5 * n + i], v2 = rays[6 * n + i];
+  HitStack S;
+  double best_t;
+  int best_leaf;
+  bool tie = false;
+  nearest_hit(sc, p0, p1, p2, v0, v1, v2, S, best_t, best_leaf, tie);
+  t_out[i] = best_t;
+  sid_out[i] = best_leaf >= 0 ? (long long)sc.leaves[best_leaf].sid : -1;
+  if (normals) {
+    double n0 = CUDART_NAN, n1 = CUDART_NAN, n2 = CUDART_NAN;
+    if (best_leaf >= 0)
+      world_normal(sc.leaves[best_leaf], p0 + v0 * best_t, p1 + v1 * best_t, p2 + v2 * best_t, n0, n1, n2);
+    normals[0 * n + i] = n0;
+    normals[1 * n + i] = n1;
+    normals[2 * n + i] = n2;
+  }
+}
+
 // ---------------------------------------------------------------- K3: seeded synthetic sources
 //
 // Counter-based uniforms u(i,k) = mix64(seed ^ (i*C1 + k*C2)) >> 11 * 2^-53; only + - * / sqrt
@@ -374,6 +409,82 @@ __global__ void source_kernel(const prt_source_desc src, double* rays, long long
   r[12 * stride] = (double)i;
 }
 
+// The reference's deterministic Source classes generated on the device:
+// _local_ray_generation of LineOfRays / CircleOfRays / ConeOfRays / WedgeOfRays
+// (pyrayt/components.py:511-613), then Source.generate_rays' world transform and direction
+// normalisation (:481-496).  p[0] = spacing | diameter | cone angle [rad] | wedge angle [rad],
+// p[1] = wavelength, p[2] = rays of this source, p[3] = id of its first ray, p[4..15] = rows 0..2
+// of the source's world matrix.  linspace / arange arithmetic follows NumPy's formulas exactly;
+// sin/cos are the CUDA double-precision functions (within 1-2 ulp of NumPy's).
+__global__ void reference_source_kernel(const prt_source_desc src, double* rays, long long stride) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)src.p[2];
+  if (j >= n) return;
+  const double jd = (double)j, nd = (double)n;
+  double lx = 0, ly = 0, lz = 0, ux = 0, uy = 0, uz = 0;
+  const double two_pi = 2 * 3.141592653589793;
+  if (src.kind == 10) {  // LineOfRays: y = linspace(-s/2, s/2, n), direction +x
+    if (n > 1) {
+      const double start = -src.p[0] / 2, stop = src.p[0] / 2;
+      const double step = (stop - start) / (nd - 1);
+      ly = (j == n - 1) ? stop : (step != 0 ? jd * step + start : jd / (nd - 1) * (stop - start) + start);
+    }
+    ux = 1;
+  } else if (src.kind == 11) {  // CircleOfRays: theta = linspace(0, 2 pi, n)
+    double th = 0;
+    if (n > 1) {
+      const double step = two_pi / (nd - 1);
+      th = (j == n - 1) ? two_pi : jd * step;
+    }
+    ly = src.p[0] / 2 * sin(th);
+    lz = src.p[0] / 2 * cos(th);
+    ux = 1;
+  } else if (src.kind == 12) {  // ConeOfRays: angles = 2 pi arange(n) / n
+    if (n > 1) {
+      const double ang = two_pi * jd / nd;
+      uy = sin(src.p[0]) * sin(ang);
+      uz = sin(src.p[0]) * cos(ang);
+    }
+    ux = cos(src.p[0]);
+  } else {  // 13 WedgeOfRays: angles = linspace(-a/2, a/2, n)
+    double ang;
+    if (n > 1) {
+      const double start = -src.p[0] / 2, stop = src.p[0] / 2;
+      const double step = (stop - start) / (nd - 1);
+      ang = (j == n - 1) ? stop : (step != 0 ? jd * step + start : jd / (nd - 1) * (stop - start) + start);
+    } else {
+      ang = -src.p[0] / 2;  // linspace(start, stop, 1) = [start]
+    }
+    ux = cos(ang);
+    uy = sin(ang);
+  }
+  const double* M = src.p + 4;
+  const double px = M[0] * lx + M[1] * ly + M[2] * lz + M[3];
+  const double py = M[4] * lx + M[5] * ly + M[6] * lz + M[7];
+  const double pz = M[8] * lx + M[9] * ly + M[10] * lz + M[11];
+  double dx = M[0] * ux + M[1] * uy + M[2] * uz;
+  double dy = M[4] * ux + M[5] * uy + M[6] * uz;
+  double dz = M[8] * ux + M[9] * uy + M[10] * uz;
+  const double nrm = sqrt(dx * dx + dy * dy + dz * dz);
+  dx /= nrm;
+  dy /= nrm;
+  dz /= nrm;
+  double* r = rays + j;
+  r[0 * stride] = px;
+  r[1 * stride] = py;
+  r[2 * stride] = pz;
+  r[3 * stride] = 1.0;
+  r[4 * stride] = dx;
+  r[5 * stride] = dy;
+  r[6 * stride] = dz;
+  r[7 * stride] = 0.0;
+  r[8 * stride] = 0.0;
+  r[9 * stride] = 100.0;
+  r[10 * stride] = src.p[1];
+  r[11 * stride] = 1.0;
+  r[12 * stride] = src.p[3] + jd;
+}
+
 // ---------------------------------------------------------------- FP64 pipe probe (roofline denominator)
 //
 // 8 independent DFMA chains per thread; bench.py times it with CUDA events to get the
@@ -452,11 +563,25 @@ cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int 
   return cudaGetLastError();
 }
 
+cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const double* rays, long long n, double* t_out,
+                               long long* sid_out, double* normals, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + prt::kTileRays - 1) / prt::kTileRays);
+  if (blob_bytes > 48 * 1024)
+    cudaFuncSetAttribute(prt::nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
+  prt::nearest_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out, sid_out,
+                                                                          normals);
+  return cudaGetLastError();
+}
+
 cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
                               long long first, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  prt::source_kernel<<<blocks, 256, 0, st>>>(*src, rays, n, stride, first);
+  if (src->kind >= 10)
+    prt::reference_source_kernel<<<blocks, 256, 0, st>>>(*src, rays, stride);
+  else
+    prt::source_kernel<<<blocks, 256, 0, st>>>(*src, rays, n, stride, first);
   return cudaGetLastError();
 }
 

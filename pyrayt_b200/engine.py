@@ -185,6 +185,28 @@ class Engine:
         host = ctr.cpu()
         return dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in host[: len(_lib.COUNTER_FIELDS)])))
 
+    # ------------------------------------------------------------------ scene updates / nearest hit
+    def update_scene(self, scene: FlatScene) -> None:
+        """Re-encode a (moved / re-parameterised) scene into this engine without re-creating it."""
+        desc = scene.as_desc()
+        with self._torch.cuda.device(self.device):
+            _lib.check(self.lib.prt_scene_update(self._handle, ctypes.byref(desc), self._stream()), "prt_scene_update")
+        self.scene = scene
+        self.n_leaves = scene.n_leaves
+
+    def nearest_hit(self, d_rays, normals: bool = False):
+        """_st_propagate alone: (distance (N,), surface id (N,), world normals (3,N) or None)."""
+        torch = self._torch
+        r = d_rays.reshape(8, -1).contiguous()
+        n = int(r.shape[1])
+        t = torch.empty(n, dtype=torch.float64, device=self._dev())
+        sid = torch.empty(n, dtype=torch.int64, device=self._dev())
+        nrm = torch.empty((3, n), dtype=torch.float64, device=self._dev()) if normals else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.prt_nearest_hit(self._handle, r.data_ptr(), n, t.data_ptr(), sid.data_ptr(),
+                                                nrm.data_ptr() if normals else None, self._stream()), "prt_nearest_hit")
+        return t, sid, nrm
+
     # ------------------------------------------------------------------ component.intersect
     def intersect(self, component: int, d_rays):
         """component.intersect(rays (2,4,N) device) -> (hits (m,N), surface ids (m,N)) device tensors."""

@@ -99,3 +99,37 @@ class ArraySource:
 
     def generate_rays(self, n):
         return self._rays[:, :n].copy()
+
+
+class _RefSource:
+    """Stand-in for the reference's deterministic sources: same class names and attributes."""
+
+    _kind = None
+    _attr = None
+
+    def __init__(self, value, wavelength=0.633, world=None):
+        setattr(self, self._attr, value)
+        self._wavelength = wavelength
+        self._world_coordinate_transform = np.eye(4) if world is None else np.asarray(world, dtype=float)
+
+    def generate_rays(self, n):
+        from oracle import sources_np
+
+        p = [getattr(self, self._attr), self._wavelength, float(n), 0.0] + list(self._world_coordinate_transform[:3].reshape(12))
+        return sources_np.reference_source(self._kind, p, n)
+
+
+class LineOfRays(_RefSource):
+    _kind, _attr = 10, "_spacing"
+
+
+class CircleOfRays(_RefSource):
+    _kind, _attr = 11, "_diameter"
+
+
+class ConeOfRays(_RefSource):
+    _kind, _attr = 12, "_angle"
+
+
+class WedgeOfRays(_RefSource):
+    _kind, _attr = 13, "_angle"

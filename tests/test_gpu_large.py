@@ -222,3 +222,31 @@ def test_drop_in_raytracer_api(torch_mod):
     bad = fakes.Surface(fakes.Sphere(1.0), fakes.Gooch(), su.translate(0, 0, 13))
     with pytest.raises(AttributeError):
         pyrayt_b200.RayTracer(fakes.ArraySource(away), [bad], rays_per_source=1).trace()
+
+
+def test_nearest_hit_and_scene_update(torch_mod):
+    """prt_nearest_hit (= _st_propagate, the renderers' per-pixel loop) and prt_scene_update."""
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+
+    scene, rays13, _, _ = load_case("thick_lens_zoo")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    rng = np.random.default_rng(5)
+    n = 20000
+    r = np.zeros((8, n))
+    r[0:3] = rng.uniform(-2, 16, (3, n)) * np.array([[1.0], [0.15], [0.15]])
+    d = rng.normal(size=(3, n)) * np.array([[1.0], [0.3], [0.3]])
+    r[3], r[4:7] = 1, d / np.linalg.norm(d, axis=0)
+    t, sid, nrm = eng.nearest_hit(torch_mod.from_numpy(r).cuda(), normals=True)
+    ot, osid, onrm = oracle.nearest(scene, r)
+    assert np.array_equal(t.cpu().numpy(), ot) and np.array_equal(sid.cpu().numpy(), osid)
+    assert np.array_equal(nrm.cpu().numpy(), onrm, equal_nan=True)
+    assert (osid >= 0).mean() > 0.3
+    # update in place: same topology, different matrices -> same results as a fresh engine
+    for seed in (1, 2):
+        s2, rays = su.random_scene_and_rays(seed, n_rays=2048)
+        eng.update_scene(s2)
+        got = eng.trace(torch_mod.from_numpy(rays).cuda(), generation_limit=12, to_host=True).frame.numpy()
+        want, _ = oracle.trace(s2, rays, 12)
+        assert np.array_equal(got, want, equal_nan=True)
