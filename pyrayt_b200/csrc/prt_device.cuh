@@ -117,7 +117,7 @@ struct RayInv {
 struct SceneView {
   const BlobHeader* h;
   const int* comp;
-  const int* shape;
+  const Comp* comps;
   const Op* ops;
   const double* aabb;
   const Leaf* leaves;
@@ -127,7 +127,7 @@ PRT_HD SceneView make_view(const unsigned char* blob) {
   SceneView s;
   s.h = reinterpret_cast<const BlobHeader*>(blob);
   s.comp = reinterpret_cast<const int*>(blob + s.h->off_comp);
-  s.shape = reinterpret_cast<const int*>(blob + s.h->off_shape);
+  s.comps = reinterpret_cast<const Comp*>(blob + s.h->off_comps);
   s.ops = reinterpret_cast<const Op*>(blob + s.h->off_ops);
   s.aabb = reinterpret_cast<const double*>(blob + s.h->off_aabb);
   s.leaves = reinterpret_cast<const Leaf*>(blob + s.h->off_leaves);
@@ -594,31 +594,29 @@ PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
   }
 }
 
-// shapes 2/3: [ENTER root][ENTER inner]? LEAF a, MERGE_LEAF(op1, b) [, MERGE_LEAF(op2, c)]
-PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0, double p1, double p2, double v0,
-                           double v1, double v2, const RayInv& inv, double best_t, double& ct, int& cl, bool& tie) {
+// shapes 2/3: (A op1 B) [op2 C] with their bounding boxes (csg.py:118-160 for a left-deep tree)
+PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double p1, double p2, double v0, double v1,
+                           double v2, const RayInv& inv, double best_t, double& ct, int& cl, bool& tie) {
   ct = PRT_INF;
   cl = -1;
-  const Op root = sc.ops[begin];
+  const int shape = C.shape;
   double b0, b1;
-  cube_hits(sc.aabb + 6 * root.a, p0, p1, p2, v0, v1, v2, inv, b0, b1);
-  if (!(b0 < PRT_INF)) return;                                                      // csg.py:126-133
-  if ((root.c & 1) && (b1 < -kCullMargin || b0 > best_t + kCullMargin)) return;    // proven-box pruning
-  int pc = begin + 1;
+  cube_hits(C.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
+  if (!(b0 < PRT_INF)) return;  // csg.py:126-133
+  // proven-box pruning: a box behind the ray or beyond the best hit so far cannot matter
+  if ((C.flags & 1) && (b1 < -kCullMargin || b0 > best_t + kCullMargin)) return;
   bool inner_hit = true;
-  if (shape == 3) {
-    const Op inner = sc.ops[pc++];
-    cube_hits(sc.aabb + 6 * inner.a, p0, p1, p2, v0, v1, v2, inv, b0, b1);
+  if (shape == SHAPE_LEFT3) {
+    cube_hits(C.inner_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
     inner_hit = b0 < PRT_INF;
   }
-  const Op oa = sc.ops[pc], ob = sc.ops[pc + 1];
-  const int lc = (shape == 3) ? sc.ops[pc + 2].b : -1;
-  const int op2 = (shape == 3) ? sc.ops[pc + 2].a : 0;
+  const int la = C.leaf_a, lb = C.leaf_b, lc = C.leaf_c;
+  const int op1 = C.op1, op2 = C.op2;
   double a0 = PRT_INF, a1 = PRT_INF, q0 = PRT_INF, q1 = PRT_INF, c0 = PRT_INF, c1 = PRT_INF;
   // one (not unrolled) loop over the leaves keeps a single copy of leaf_hits in the hot loop
 #pragma unroll 1
   for (int k = inner_hit ? 0 : 2; k < shape; ++k) {
-    const int lf = (k == 0) ? oa.a : ((k == 1) ? ob.b : lc);
+    const int lf = (k == 0) ? la : ((k == 1) ? lb : lc);
     double t0, t1;
     leaf_hits(sc.leaves[lf], p0, p1, p2, v0, v1, v2, t0, t1);
     if (k == 0) {
@@ -634,12 +632,12 @@ PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0,
   }
   bool keep[4] = {false, false, false, false};
   int pos[4] = {0, 1, 2, 3};
-  if (inner_hit) merge22(ob.a, a0, a1, q0, q1, keep, pos, tie);
-  if (shape == 2) {
-    take_hit(keep[0], a0, oa.a, ct, cl);
-    take_hit(keep[1], a1, oa.a, ct, cl);
-    take_hit(keep[2], q0, ob.b, ct, cl);
-    take_hit(keep[3], q1, ob.b, ct, cl);
+  if (inner_hit) merge22(op1, a0, a1, q0, q1, keep, pos, tie);
+  if (shape == SHAPE_LEFT2) {
+    take_hit(keep[0], a0, la, ct, cl);
+    take_hit(keep[1], a1, la, ct, cl);
+    take_hit(keep[2], q0, lb, ct, cl);
+    take_hit(keep[3], q1, lb, ct, cl);
     return;
   }
   // second merge: left = the kept entries of the first merge (index = number of kept entries before
@@ -669,59 +667,59 @@ PRT_HD void eval_left_deep(const SceneView& sc, int begin, int shape, double p0,
   const bool kc0 = vc0 && csg_keep(op2, cnt, cnt - sR);
   cnt = start + (lb1 & 1);
   const bool kc1 = vc1 && csg_keep(op2, cnt, cnt + sR);
-  take_hit(keep2[0], a0, oa.a, ct, cl);
-  take_hit(keep2[1], a1, oa.a, ct, cl);
-  take_hit(keep2[2], q0, ob.b, ct, cl);
-  take_hit(keep2[3], q1, ob.b, ct, cl);
+  take_hit(keep2[0], a0, la, ct, cl);
+  take_hit(keep2[1], a1, la, ct, cl);
+  take_hit(keep2[2], q0, lb, ct, cl);
+  take_hit(keep2[3], q1, lb, ct, cl);
   take_hit(kc0, c0, lc, ct, cl);
   take_hit(kc1, c1, lc, ct, cl);
 }
 
-// nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386)
-PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0,
-                                            double v1, double v2, HitStack& S, double& best_t, int& best_leaf,
-                                            bool& tie) {
+// nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386); components are
+// visited in order (the earlier one wins ties)
+PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0, double v1, double v2,
+                        HitStack& S, double& best_t, int& best_leaf, bool& tie) {
   best_t = PRT_INF;
   best_leaf = -1;
   const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
   const int nc = sc.h->n_components;
-  for (int c = 0; c < nc; ++c) {
-    const int begin = sc.comp[c], end = sc.comp[c + 1];
-    const int shape = sc.shape[c];
-    if (shape == SHAPE_LEAF) {
-      // bare TracerSurface component: no list needed
-      const Op first = sc.ops[begin];
-      double t0, t1;
-      leaf_hits(sc.leaves[first.a], p0, p1, p2, v0, v1, v2, t0, t1);
-      const double t = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
-      if (t < best_t) {
-        best_t = t;
-        best_leaf = first.a;
-      }
-      continue;
-    }
-    if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
-      double ct;
-      int cl;
-      eval_left_deep(sc, begin, shape, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
-      if (ct < best_t) {  // strict: the earlier component wins ties (:384)
-        best_t = ct;
-        best_leaf = cl;
-      }
-      continue;
-    }
-    S.flags = 0;
-    if (!eval_component(sc, begin, end, p0, p1, p2, v0, v1, v2, inv, true, best_t, S, tie)) continue;
-    const int b = buf_of(S, 0);
-    const int n = S.len[0];
-    for (int k = 0; k < n; ++k) {  // sorted: the first positive entry is the argmin of where(hits>0)
-      const double t = S.t[b][k];
-      if (t > 0) {
-        if (t < best_t) {  // strict: the earlier component wins ties (:384)
+  {
+    for (int c = 0; c < nc; ++c) {
+      const Comp& C = sc.comps[c];
+      const int shape = C.shape;
+      if (shape == SHAPE_LEAF) {  // bare TracerSurface component: no list needed
+        double t0, t1;
+        leaf_hits(sc.leaves[C.leaf_a], p0, p1, p2, v0, v1, v2, t0, t1);
+        const double t = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
+        if (t < best_t) {
           best_t = t;
-          best_leaf = S.leaf[b][k];
+          best_leaf = C.leaf_a;
         }
-        break;
+        continue;
+      }
+      if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
+        double ct;
+        int cl;
+        eval_left_deep(sc, C, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
+        if (ct < best_t) {  // strict: the earlier component wins ties (:384)
+          best_t = ct;
+          best_leaf = cl;
+        }
+        continue;
+      }
+      S.flags = 0;
+      if (!eval_component(sc, C.begin, C.end, p0, p1, p2, v0, v1, v2, inv, true, best_t, S, tie)) continue;
+      const int b = buf_of(S, 0);
+      const int n = S.len[0];
+      for (int j = 0; j < n; ++j) {  // sorted: the first positive entry is the argmin of where(hits>0)
+        const double t = S.t[b][j];
+        if (t > 0) {
+          if (t < best_t) {
+            best_t = t;
+            best_leaf = S.leaf[b][j];
+          }
+          break;
+        }
       }
     }
   }

@@ -156,7 +156,7 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   Encoder enc;
   enc.s = d;
   std::vector<int> comp_begin(d->n_components + 1, 0);
-  std::vector<int> comp_shape;
+  std::vector<prt::Comp> comps;
   comp_slots.assign(d->n_components, 0);
   int max_slots = 2;
   for (int c = 0; c < d->n_components; ++c) {
@@ -200,9 +200,34 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
       else if (len == 5 && o[0].kind == prt::OP_ENTER && o[1].kind == prt::OP_ENTER && o[2].kind == prt::OP_LEAF &&
                o[3].kind == prt::OP_MERGE_LEAF && o[4].kind == prt::OP_MERGE_LEAF)
         shape = prt::SHAPE_LEFT3;
-      comp_shape.push_back(shape);
+      prt::Comp C;
+      std::memset(&C, 0, sizeof C);
+      C.shape = shape;
+      C.begin = comp_begin[c];
+      C.end = (int)enc.ops.size();
+      C.leaf_a = C.leaf_b = C.leaf_c = -1;
+      if (shape == prt::SHAPE_LEAF) C.leaf_a = o[0].a;
+      if (shape == prt::SHAPE_LEFT2) {
+        C.leaf_a = o[1].a;
+        C.leaf_b = o[2].b;
+        C.op1 = o[2].a;
+        for (int k = 0; k < 6; ++k) C.root_box[k] = enc.aabb[6 * o[0].a + k];
+      }
+      if (shape == prt::SHAPE_LEFT3) {
+        C.leaf_a = o[2].a;
+        C.leaf_b = o[3].b;
+        C.leaf_c = o[4].b;
+        C.op1 = o[3].a;
+        C.op2 = o[4].a;
+        for (int k = 0; k < 6; ++k) C.root_box[k] = enc.aabb[6 * o[0].a + k];
+        for (int k = 0; k < 6; ++k) C.inner_box[k] = enc.aabb[6 * o[1].a + k];
+      }
+      comps.push_back(C);
     }
-    if (enc.tree[root].kind != PRT_LEAF && enc.root_box_is_bound(root)) enc.ops[comp_begin[c]].c |= 1;
+    if (enc.tree[root].kind != PRT_LEAF && enc.root_box_is_bound(root)) {
+      enc.ops[comp_begin[c]].c |= 1;
+      comps.back().flags |= 1;
+    }
   }
   comp_begin[d->n_components] = (int)enc.ops.size();
   if (enc.max_depth > prt::kMaxDepth) return fail(PRT_ERR_LIMIT, "CSG tree nests too deeply on the right");
@@ -232,13 +257,14 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
       if (!(v == 0.0 || (av >= 0x1p-823 && av < 0x1p677))) tame = false;
     }
     h.flags = tame ? 1 : 0;
+
   }
   auto align8 = [](int x) { return (x + 7) & ~7; };
   int off = align8((int)sizeof(prt::BlobHeader));
   h.off_comp = off;
   off = align8(off + (int)sizeof(int) * (d->n_components + 1));
-  h.off_shape = off;
-  off = align8(off + (int)sizeof(int) * (d->n_components > 0 ? d->n_components : 1));
+  h.off_comps = off;
+  off = align8(off + (int)sizeof(prt::Comp) * (d->n_components > 0 ? d->n_components : 1));
   h.off_ops = off;
   off = align8(off + (int)sizeof(prt::Op) * h.n_ops);
   h.off_aabb = off;
@@ -249,7 +275,7 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   blob.assign((size_t)off, 0);
   std::memcpy(blob.data(), &h, sizeof h);
   std::memcpy(blob.data() + h.off_comp, comp_begin.data(), sizeof(int) * comp_begin.size());
-  if (!comp_shape.empty()) std::memcpy(blob.data() + h.off_shape, comp_shape.data(), sizeof(int) * comp_shape.size());
+  if (!comps.empty()) std::memcpy(blob.data() + h.off_comps, comps.data(), sizeof(prt::Comp) * comps.size());
   if (h.n_ops) std::memcpy(blob.data() + h.off_ops, enc.ops.data(), sizeof(prt::Op) * enc.ops.size());
   if (h.n_aabb) std::memcpy(blob.data() + h.off_aabb, enc.aabb.data(), sizeof(double) * enc.aabb.size());
   prt::Leaf* leaves = reinterpret_cast<prt::Leaf*>(blob.data() + h.off_leaves);

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned cha
   S.flags = 0;
   bool tie = false;
   const bool any =
-      eval_component(sc, sc.comp[component], sc.comp[component + 1], p0, p1, p2, v0, v1, v2,
+      eval_component(sc, sc.comps[component].begin, sc.comps[component].end, p0, p1, p2, v0, v1, v2,
                      make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0), false, PRT_INF, S, tie);
   const int b = buf_of(S, 0);
   const int len = any ? S.len[0] : 0;

@@ -39,6 +39,20 @@ enum Shape : int {
   SHAPE_LEFT3 = 3     // ENTER, ENTER, LEAF a, MERGE_LEAF b, MERGE_LEAF c  ((A op1 B) op2 C)
 };
 
+// Everything nearest_hit needs about one component, in one place (no pointer chasing through the
+// op list): shape, proven-bound flag, the op range for the generic interpreter and, for the
+// left-deep shapes, the leaves, operations and both bounding boxes.
+struct Comp {
+  int shape;   // Shape
+  int flags;   // bit 0: the root box provably contains the solid -> pruning allowed
+  int begin, end;                  // ops [begin, end)
+  int leaf_a, leaf_b, leaf_c;      // SHAPE_LEAF: leaf_a; SHAPE_LEFT2: a, b; SHAPE_LEFT3: a, b, c
+  int op1, op2;                    // (A op1 B) op2 C
+  int pad[3];
+  double root_box[6];
+  double inner_box[6];             // SHAPE_LEFT3: box of (A op1 B)
+};
+
 struct Op {
   int kind, a, b, c;
 };
@@ -62,7 +76,7 @@ struct BlobHeader {
   int total_bytes;
   int max_slots;   // largest component hit-list length
   int flags;       // bit 0: every bounding-box span is 0 or in [2^-823, 2^677) (fast slab test allowed)
-  int off_shape;   // int[n_components] : Shape per component
+  int off_comps;   // Comp[n_components]
 };
 
 // arguments of the trace kernel (filled by prt_trace)

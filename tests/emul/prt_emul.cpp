@@ -81,7 +81,7 @@ int prt_emul_intersect(const prt_scene_desc* d, int comp, const double* rays, lo
     S.flags = 0;
     bool tie = false;
     const bool any = prt::eval_component(
-        sc, sc.comp[comp], sc.comp[comp + 1], rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i],
+        sc, sc.comps[comp].begin, sc.comps[comp].end, rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i],
         rays[5 * n + i], rays[6 * n + i],
         prt::make_ray_inv(rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i], rays[5 * n + i],
                           rays[6 * n + i], (sc.h->flags & 1) != 0),
@@ -104,8 +104,7 @@ int prt_emul_prune_flags(const prt_scene_desc* d, int* flags) {
   if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
   const prt::SceneView sc = prt::make_view(blob.data());
   for (int c = 0; c < sc.h->n_components; ++c) {
-    const prt::Op first = sc.ops[sc.comp[c]];
-    flags[c] = (first.kind == prt::OP_ENTER) ? (first.c & 1) : -1;
+    flags[c] = (sc.comps[c].shape == prt::SHAPE_LEAF) ? -1 : (sc.comps[c].flags & 1);
   }
   return 0;
 }
