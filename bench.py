@@ -278,6 +278,7 @@ def main():
             t = json.load(fh)
         if t.get("workload") == wl.name and t.get("rays") == n:
             roof["traffic"] = t.get("dram_bytes_per_launch")
+            roof["traffic_source"] = t.get("source")
 
     # ------------------------------------------------------------------ end to end through host buffers
     e2e = None
