@@ -141,6 +141,7 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
   if (n_rays < 0 || (n_rays > 0 && !d_rays)) return fail(PRT_ERR_INVALID, "bad ray buffer");
   if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
   if (p->generation_limit < 1) return fail(PRT_ERR_INVALID, "generation_limit must be >= 1");
+  if (p->generation_limit > 65535) return fail(PRT_ERR_LIMIT, "generation_limit must be <= 65535");
   if (p->record_mode < PRT_RECORD_ALL || p->record_mode > PRT_RECORD_NONE)
     return fail(PRT_ERR_INVALID, "bad record_mode");
   const int64_t tiles = (n_rays + prt::kTileRays - 1) / prt::kTileRays;

@@ -729,7 +729,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
 // ---------------------------------------------------------------- one generation of one ray
 
 struct RayState {
-  double p0, p1, p2, v0, v1, v2, gen, inten, wl, nidx, id;
+  double p0, p1, p2, v0, v1, v2, wl, nidx;  // generation / intensity / id are only copied to the rows
 };
 
 struct StepOut {
@@ -741,9 +741,13 @@ struct StepOut {
   double n_next;             // refractive index after the interaction
 };
 
+// per-ray event counters packed into two words (they stay live for the whole kernel):
+// w0 = generations entered | rows << 16 ; w1 = mirror rows | flag bits.  generation_limit <= 65535.
 struct StepCounters {
-  unsigned gen, seg, tie, untr, nan, lim, seg_abs, seg_mir;
+  unsigned w0, w1;
 };
+constexpr unsigned kCtrTie = 1u << 16, kCtrUntr = 1u << 17, kCtrNan = 1u << 18, kCtrLim = 1u << 19,
+                   kCtrAbs = 1u << 20;
 
 // _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
 // returns true when the ray goes on to generation g+1.
@@ -753,15 +757,15 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   const double vn = sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
   if (isz(vn)) return false;  // absorbed / zero direction (_pyrayt.py:415)
   if (isnan(r.v0) || isnan(r.v1) || isnan(r.v2)) {
-    c.nan++;  // every hit compares false in the reference -> miss
+    c.w1 |= kCtrNan;  // every hit compares false in the reference -> miss
     return false;
   }
-  c.gen++;
+  c.w0 += 1u;
   double best_t;
   int best_leaf;
   bool tie = false;
   nearest_hit(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, S, best_t, best_leaf, tie);
-  if (tie) c.tie = 1;
+  if (tie) c.w1 |= kCtrTie;
   if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
   const Leaf& L = sc.leaves[best_leaf];
   o.e0 = r.p0 + r.v0 * best_t;  // :404-407
@@ -779,10 +783,10 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
     o.nv1 = 0;
     o.nv2 = 0;
     goes_on = false;  // recorded now, dead next generation (zero direction)
-    c.seg_abs++;
+    c.w1 |= kCtrAbs;
   } else if (L.mat == PRT_MAT_MIRROR) {  // materials.py:58-62, operations.py:105-107
     double n0, n1, n2;
-    c.seg_mir++;
+    c.w1 += 1u;
     world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
     const double dots = r.v0 * n0 + r.v1 * n1 + r.v2 * n2;
     o.nv0 = r.v0 - 2 * n0 * dots;
@@ -829,14 +833,14 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
     o.nv1 = div_by(o.nv1, nn);
     o.nv2 = div_by(o.nv2, nn);
   } else {
-    c.untr++;  // the reference raises AttributeError here
+    c.w1 |= kCtrUntr;  // the reference raises AttributeError here
     return false;
   }
-  c.seg++;
+  c.w0 += 1u << 16;
   o.row = true;
   o.sid = L.sid;
   if (g + 1 == generation_limit) {
-    c.lim++;
+    c.w1 |= kCtrLim;
     return false;
   }
   return goes_on;
@@ -844,7 +848,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
 
 // generation g -> g+1 (pyrayt/_pyrayt.py:436-449)
 PRT_HD void advance_ray(RayState& r, const StepOut& o, int g, double ray_offset) {
-  r.gen = (double)(g + 1);
+  (void)g;
   r.nidx = o.n_next;
   r.v0 = o.nv0;
   r.v1 = o.nv1;

@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   extern __shared__ __align__(16) unsigned char s_blob[];
   __shared__ int s_wcount[kTileRays / 32];
   __shared__ long long s_base;
+  // per-ray values only needed when a row is written live in shared memory, not in registers
+  __shared__ double s_gen0[kTileRays], s_inten[kTileRays], s_id[kTileRays];
 
   // stage the scene in shared memory once per block
   {
@@ -56,8 +58,8 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
-  RayState rs = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
-  StepCounters sc_ctr = {0, 0, 0, 0, 0, 0, 0, 0};
+  RayState rs = {0, 0, 0, 0, 0, 0, 0, 1};
+  StepCounters sc_ctr = {0, 0};
   unsigned c_drop = 0, c_badw = 0;
   if (valid) {
     const double* r = a.rays + i;
@@ -69,11 +71,11 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
     rs.v1 = r[5 * a.stride];
     rs.v2 = r[6 * a.stride];
     const double vw = r[7 * a.stride];
-    rs.gen = r[8 * a.stride];
-    rs.inten = r[9 * a.stride];
+    s_gen0[threadIdx.x] = r[8 * a.stride];
+    s_inten[threadIdx.x] = r[9 * a.stride];
     rs.wl = r[10 * a.stride];
     rs.nidx = r[11 * a.stride];
-    rs.id = r[12 * a.stride];
+    s_id[threadIdx.x] = r[12 * a.stride];
     if (pw != 1.0 || vw != 0.0) c_badw = 1;
   }
   bool alive = valid;
@@ -116,11 +118,11 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
           const long long row = run + before + __popc(m & ((1u << lane) - 1u));
           double* o = a.stage + row;
           const long long cs = a.capacity;
-          o[0 * cs] = rs.gen;
-          o[1 * cs] = rs.inten;
+          o[0 * cs] = (g == 0) ? s_gen0[threadIdx.x] : (double)g;  // :440-441
+          o[1 * cs] = s_inten[threadIdx.x];
           o[2 * cs] = rs.wl;
           o[3 * cs] = rs.nidx;
-          o[4 * cs] = rs.id;
+          o[4 * cs] = s_id[threadIdx.x];
           o[5 * cs] = so.sid;
           o[6 * cs] = rs.p0;
           o[7 * cs] = rs.p1;
@@ -147,9 +149,17 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   }
 
   // counters: warp-reduce, one atomic per warp and counter
-  unsigned long long vals[11] = {valid ? 1ull : 0ull, sc_ctr.gen, sc_ctr.seg, c_drop, sc_ctr.tie ? 1ull : 0ull,
-                                 sc_ctr.untr,         c_badw,     sc_ctr.nan, sc_ctr.lim, sc_ctr.seg_abs,
-                                 sc_ctr.seg_mir};
+  unsigned long long vals[11] = {valid ? 1ull : 0ull,
+                                 sc_ctr.w0 & 0xffffu,
+                                 sc_ctr.w0 >> 16,
+                                 c_drop,
+                                 (sc_ctr.w1 & kCtrTie) ? 1ull : 0ull,
+                                 (sc_ctr.w1 & kCtrUntr) ? 1ull : 0ull,
+                                 c_badw,
+                                 (sc_ctr.w1 & kCtrNan) ? 1ull : 0ull,
+                                 (sc_ctr.w1 & kCtrLim) ? 1ull : 0ull,
+                                 (sc_ctr.w1 & kCtrAbs) ? 1ull : 0ull,
+                                 sc_ctr.w1 & 0xffffu};
   unsigned long long* dst[11] = {
       reinterpret_cast<unsigned long long*>(&a.ctr->rays),
       reinterpret_cast<unsigned long long*>(&a.ctr->generations),

@@ -28,24 +28,25 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
   const prt::SceneView sc = prt::make_view(blob.data());
   long long total = 0;
-  prt::StepCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
-  unsigned long long tie_rays = 0;
+  prt::StepCounters c = {0, 0};
+  unsigned long long tie_rays = 0, gens = 0, segs = 0, untr = 0, nans = 0, lims = 0;
   for (long long i = 0; i < n; ++i) {
     prt::RayState r;
     r.p0 = rays[0 * stride + i]; r.p1 = rays[1 * stride + i]; r.p2 = rays[2 * stride + i];
     r.v0 = rays[4 * stride + i]; r.v1 = rays[5 * stride + i]; r.v2 = rays[6 * stride + i];
-    r.gen = rays[8 * stride + i]; r.inten = rays[9 * stride + i]; r.wl = rays[10 * stride + i];
-    r.nidx = rays[11 * stride + i]; r.id = rays[12 * stride + i];
+    const double gen0 = rays[8 * stride + i], inten = rays[9 * stride + i], id = rays[12 * stride + i];
+    r.wl = rays[10 * stride + i];
+    r.nidx = rays[11 * stride + i];
     prt::HitStack S;
     int k = 0;
-    c.tie = 0;
+    c.w1 &= ~prt::kCtrTie;
     for (int g = 0; g < generation_limit; ++g) {
       prt::StepOut o;
       const bool on = prt::trace_step(sc, r, g, generation_limit, S, o, c);
       if (o.row) {
         if (total < cap) {
           double* w = rows_out + total * 15;
-          w[0] = r.gen; w[1] = r.inten; w[2] = r.wl; w[3] = r.nidx; w[4] = r.id; w[5] = o.sid;
+          w[0] = (g == 0) ? gen0 : (double)g; w[1] = inten; w[2] = r.wl; w[3] = r.nidx; w[4] = id; w[5] = o.sid;
           w[6] = r.p0; w[7] = r.p1; w[8] = r.p2; w[9] = o.e0; w[10] = o.e1; w[11] = o.e2;
           w[12] = o.t0n; w[13] = o.t1n; w[14] = o.t2n;
         }
@@ -55,16 +56,23 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
       if (!on) break;
       prt::advance_ray(r, o, g, ray_offset);
     }
-    tie_rays += c.tie;
+    tie_rays += (c.w1 & prt::kCtrTie) ? 1 : 0;
+    gens += c.w0 & 0xffffu;
+    segs += c.w0 >> 16;
+    untr += (c.w1 & prt::kCtrUntr) ? 1 : 0;
+    nans += (c.w1 & prt::kCtrNan) ? 1 : 0;
+    lims += (c.w1 & prt::kCtrLim) ? 1 : 0;
+    c.w0 = 0;
+    c.w1 = 0;
     nrows[i] = k;
   }
   counters[0] = (unsigned long long)n;
-  counters[1] = c.gen;
-  counters[2] = c.seg;
+  counters[1] = gens;
+  counters[2] = segs;
   counters[3] = tie_rays;
-  counters[4] = c.untr;
-  counters[5] = c.nan;
-  counters[6] = c.lim;
+  counters[4] = untr;
+  counters[5] = nans;
+  counters[6] = lims;
   return total;
 }
 
