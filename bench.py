@@ -19,7 +19,6 @@ bounded sample of the same workload; the Python reference itself cannot travel t
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -57,48 +56,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons of one GPU sampled (NVML, every 20 ms) during the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.thread, self.err = index, [], False, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # NVML missing: report it, never fail the bench
+            self.nv, self.err = None, repr(exc)
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception as exc:
+                self.err = repr(exc)
+                return
+            time.sleep(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.err}
+        load = [s for s in self.samples if not (s[1] & 0x1)] or self.samples  # drop "GPU idle" samples
+        mhz = sorted(s[0] for s in load)
+        bits = 0
+        for _, r in load:
+            bits |= r
+        return {"sm_mhz": float(mhz[len(mhz) // 2]), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(load)}
 
 
 def cpu_reference_run(workload, n_sample, threads, steps, warmup):
@@ -189,6 +201,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_node = pdist.bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
 
     wl = workloads.WORKLOADS[args.workload]
     n = args.rays or wl.n_rays
@@ -282,6 +295,7 @@ def main():
 
     # ------------------------------------------------------------------ end to end through host buffers
     e2e = None
+    res = None  # drop the device frame of the last resident step before the host-buffer run
     if not args.no_e2e:
         e2e = run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ranks)
 
@@ -302,7 +316,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.name, "description": wl.description, "rays_per_gpu": n,
                        "generation_limit": G, "leaves": scene.n_leaves, "rows_per_ray": rows / n,
-                       "parallelism": f"ray-range x{world}", "l2": "inputs larger than L2 (rays + staging >> 126 MB)"},
+                       "parallelism": f"ray-range x{world}", "numa_node_rank0": numa_node, "l2": "inputs larger than L2 (rays + staging >> 126 MB)"},
             "ray_surface_tests_per_s": tests_per_s, "segments_per_s": world * rows / (ms_per_step * 1e-3),
             "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,

@@ -14,7 +14,7 @@
 
 
 extern "C" {
-cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, cudaStream_t st);
+cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, cudaStream_t st);
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
                             long long* gen_offsets, cudaStream_t st);
 cudaError_t prt_launch_gather(const double* stage, long long capacity, const long long* run_start,
@@ -37,6 +37,7 @@ struct prt_scene {
   int n_leaves = 0;
   int n_components = 0;
   std::vector<int> comp_slots;
+  int generic = 1;  // some component needs the interpreter for arbitrary CSG trees
   std::vector<unsigned char> staging;  // host copy of the last prt_scene_update (pageable -> the copy is synchronous enough)
 };
 
@@ -82,6 +83,7 @@ int prt_scene_create(const prt_scene_desc* d, int device, prt_scene** out) {
   sc->n_leaves = d->n_leaves;
   sc->n_components = d->n_components;
   sc->comp_slots = comp_slots;
+  sc->generic = (reinterpret_cast<const prt::BlobHeader*>(blob.data())->flags & 2) ? 1 : 0;
   e = cudaMalloc(&sc->d_blob, (size_t)off);
   if (e != cudaSuccess) {
     delete sc;
@@ -124,6 +126,7 @@ int prt_scene_update(prt_scene* sc, const prt_scene_desc* d, void* cuda_stream) 
   sc->n_leaves = d->n_leaves;
   sc->n_components = d->n_components;
   sc->comp_slots = comp_slots;
+  sc->generic = (reinterpret_cast<const prt::BlobHeader*>(sc->staging.data())->flags & 2) ? 1 : 0;
   return PRT_OK;
 }
 
@@ -170,7 +173,7 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
   a.n_rays = n_rays;
   a.stride = ray_stride;
   a.ctr = d_counters;
-  cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, (cudaStream_t)cuda_stream);
+  cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, scene->generic, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "trace kernel launch");
   return PRT_OK;
 }

@@ -677,8 +677,11 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
 
 // nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386); components are
 // visited in order (the earlier one wins ties)
+// GENERIC = false compiles the interpreter for arbitrary trees out: scenes whose components are all
+// bare leaves or left-deep (every reference factory) run a smaller kernel with no lists in memory.
+template <bool GENERIC>
 PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0, double v1, double v2,
-                        HitStack& S, double& best_t, int& best_leaf, bool& tie) {
+                        HitStack* S, double& best_t, int& best_leaf, bool& tie) {
   best_t = PRT_INF;
   best_leaf = -1;
   const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
@@ -707,18 +710,20 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
         }
         continue;
       }
-      S.flags = 0;
-      if (!eval_component(sc, C.begin, C.end, p0, p1, p2, v0, v1, v2, inv, true, best_t, S, tie)) continue;
-      const int b = buf_of(S, 0);
-      const int n = S.len[0];
-      for (int j = 0; j < n; ++j) {  // sorted: the first positive entry is the argmin of where(hits>0)
-        const double t = S.t[b][j];
-        if (t > 0) {
-          if (t < best_t) {
-            best_t = t;
-            best_leaf = S.leaf[b][j];
+      if (GENERIC) {
+        S->flags = 0;
+        if (!eval_component(sc, C.begin, C.end, p0, p1, p2, v0, v1, v2, inv, true, best_t, *S, tie)) continue;
+        const int b = buf_of(*S, 0);
+        const int n = S->len[0];
+        for (int j = 0; j < n; ++j) {  // sorted: the first positive entry is the argmin of where(hits>0)
+          const double t = S->t[b][j];
+          if (t > 0) {
+            if (t < best_t) {
+              best_t = t;
+              best_leaf = S->leaf[b][j];
+            }
+            break;
           }
-          break;
         }
       }
     }
@@ -751,7 +756,8 @@ constexpr unsigned kCtrTie = 1u << 16, kCtrUntr = 1u << 17, kCtrNan = 1u << 18, 
 
 // _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
 // returns true when the ray goes on to generation g+1.
-PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int generation_limit, HitStack& S,
+template <bool GENERIC>
+PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int generation_limit, HitStack* S,
                        StepOut& o, StepCounters& c) {
   o.row = false;
   const double vn = sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
@@ -764,7 +770,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   double best_t;
   int best_leaf;
   bool tie = false;
-  nearest_hit(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, S, best_t, best_leaf, tie);
+  nearest_hit<GENERIC>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, S, best_t, best_leaf, tie);
   if (tie) c.w1 |= kCtrTie;
   if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
   const Leaf& L = sc.leaves[best_leaf];

@@ -257,6 +257,8 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
       if (!(v == 0.0 || (av >= 0x1p-823 && av < 0x1p677))) tame = false;
     }
     h.flags = tame ? 1 : 0;
+    for (const prt::Comp& C : comps)
+      if (C.shape == prt::SHAPE_GENERIC) h.flags |= 2;
 
   }
   auto align8 = [](int x) { return (x + 7) & ~7; };

@@ -30,11 +30,22 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
   return v;
 }
 
+template <bool GENERIC>
+struct StackFor {
+  typedef HitStack type;
+  __device__ static HitStack* ptr(HitStack& s) { return &s; }
+};
+template <>
+struct StackFor<false> {
+  typedef char type;
+  __device__ static HitStack* ptr(char&) { return nullptr; }
+};
+
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 2
 #endif
 
-template <bool RECORD>
+template <bool RECORD, bool GENERIC>
 __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char s_blob[];
   __shared__ int s_wcount[kTileRays / 32];
@@ -79,14 +90,16 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
     if (pw != 1.0 || vw != 0.0) c_badw = 1;
   }
   bool alive = valid;
-  HitStack S;
+  // hit lists for the generic interpreter only; the left-deep variant keeps everything in registers
+  typename StackFor<GENERIC>::type stack_storage;
+  HitStack* S = StackFor<GENERIC>::ptr(stack_storage);
 
   for (int g = 0; g < a.generation_limit; ++g) {
     StepOut so;
     bool write = false;
     bool next_alive = false;
     if (alive) {
-      next_alive = trace_step(sc, rs, g, a.generation_limit, S, so, sc_ctr);
+      next_alive = trace_step<GENERIC>(sc, rs, g, a.generation_limit, S, so, sc_ctr);
       alive = so.row;
       write = RECORD && so.row && (a.record_mode == PRT_RECORD_ALL || so.sid == a.detector_sid);
     }
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) nearest_kernel(cons
   double best_t;
   int best_leaf;
   bool tie = false;
-  nearest_hit(sc, p0, p1, p2, v0, v1, v2, S, best_t, best_leaf, tie);
+  nearest_hit<true>(sc, p0, p1, p2, v0, v1, v2, &S, best_t, best_leaf, tie);
   t_out[i] = best_t;
   sid_out[i] = best_leaf >= 0 ? (long long)sc.leaves[best_leaf].sid : -1;
   if (normals) {
@@ -522,22 +535,27 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters,
 
 // ---------------------------------------------------------------- launchers used by prt_abi.cpp
 
+template <bool RECORD, bool GENERIC>
+static cudaError_t launch_trace_variant(const prt::TraceArgs* a, unsigned tiles, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(prt::trace_kernel<RECORD, GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  prt::trace_kernel<RECORD, GENERIC><<<tiles, prt::kTileRays, smem, st>>>(*a);
+  return cudaGetLastError();
+}
+
 extern "C" {
 
-cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, cudaStream_t st) {
+// generic != 0: some component needs the interpreter for arbitrary CSG trees
+cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, cudaStream_t st) {
   const long long tiles = (a->n_rays + prt::kTileRays - 1) / prt::kTileRays;
   if (tiles == 0) return cudaSuccess;
   const size_t smem = (size_t)a->blob_bytes;
   if (record) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(prt::trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prt::trace_kernel<true><<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a);
-  } else {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(prt::trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prt::trace_kernel<false><<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a);
+    return generic ? launch_trace_variant<true, true>(a, (unsigned)tiles, smem, st)
+                   : launch_trace_variant<true, false>(a, (unsigned)tiles, smem, st);
   }
-  return cudaGetLastError();
+  return generic ? launch_trace_variant<false, true>(a, (unsigned)tiles, smem, st)
+                 : launch_trace_variant<false, false>(a, (unsigned)tiles, smem, st);
 }
 
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,

@@ -76,6 +76,7 @@ struct BlobHeader {
   int total_bytes;
   int max_slots;   // largest component hit-list length
   int flags;       // bit 0: every bounding-box span is 0 or in [2^-823, 2^677) (fast slab test allowed)
+                   // bit 1: some component has SHAPE_GENERIC (needs the interpreter kernel variant)
   int off_comps;   // Comp[n_components]
 };
 

@@ -104,3 +104,36 @@ def detector_summary(frame, detector_sid: int, device=None) -> Optional[dict]:
     cy, cz = acc[1] / acc[0], acc[2] / acc[0]
     rms = float(np.sqrt(max(0.0, acc[3] / acc[0] - cy * cy + acc[4] / acc[0] - cz * cz)))
     return {"count": int(acc[0]), "centroid": (float(cy), float(cz)), "rms_radius": rms}
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (one process per GPU).
+
+    Pinned host buffers are then allocated on the local node (first touch), which matters when
+    eight ranks each copy a 36 GB frame to the host at the same time.  Returns the node or None.
+    """
+    import glob
+    import os
+
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(device_index)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        nodes = glob.glob("/sys/devices/system/node/node[0-9]*")
+        if node < 0 or len(nodes) < 2:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None

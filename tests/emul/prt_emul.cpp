@@ -42,7 +42,7 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
     c.w1 &= ~prt::kCtrTie;
     for (int g = 0; g < generation_limit; ++g) {
       prt::StepOut o;
-      const bool on = prt::trace_step(sc, r, g, generation_limit, S, o, c);
+      const bool on = prt::trace_step<true>(sc, r, g, generation_limit, &S, o, c);
       if (o.row) {
         if (total < cap) {
           double* w = rows_out + total * 15;
