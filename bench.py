@@ -296,6 +296,7 @@ def main():
     # ------------------------------------------------------------------ end to end through host buffers
     e2e = None
     res = None  # drop the device frame of the last resident step before the host-buffer run
+    torch.cuda.empty_cache()
     if not args.no_e2e:
         e2e = run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ranks)
 

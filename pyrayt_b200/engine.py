@@ -85,6 +85,8 @@ class Engine:
         return t
 
     def release_workspace(self) -> None:
+        if self._torch.cuda.is_available():
+            self._torch.cuda.synchronize(self.device)
         self._ws.clear()
 
     # ------------------------------------------------------------------ trace

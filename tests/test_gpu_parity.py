@@ -32,3 +32,57 @@ def test_golden_case_matches_reference_and_oracle(name, cuda_device):
     assert res.counters["generations"] == octr["generations"]
     assert res.counters["limit_rays"] == octr["limit_rays"]
     assert res.counters["rows_dropped"] == 0 and res.counters["bad_w"] == 0
+
+
+def test_edge_inputs(cuda_device):
+    """Empty input, one ray, generation_limit 1, ray counts around the tile size, dead-on-arrival rays."""
+    import torch
+
+    import pyrayt_b200
+    from oracle import oracle
+
+    scene, rays, _, gl = load_case("thick_lens_zoo")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    for n in (0, 1, 255, 256, 257, 513):
+        for g in (1, 3, gl):
+            sub = np.ascontiguousarray(rays[:, :n])
+            res = eng.trace(torch.from_numpy(sub).cuda(), generation_limit=g, to_host=True)
+            want, octr = oracle.trace(scene, sub, g)
+            assert res.frame.shape == (15, want.shape[1])
+            assert np.array_equal(res.frame.numpy(), want, equal_nan=True), (n, g)
+            assert res.counters["limit_rays"] == octr["limit_rays"]
+    # zero-direction and NaN-direction rays never produce a row; a bad w row is counted
+    bad = np.ascontiguousarray(rays[:, :8]).copy()
+    bad[4:7, 0] = 0.0
+    bad[4:7, 1] = np.nan
+    bad[3, 2] = 0.5
+    res = eng.trace(torch.from_numpy(bad).cuda(), generation_limit=gl, to_host=True)
+    want, octr = oracle.trace(scene, bad, gl)
+    ids = set(res.frame.numpy()[4].astype(int))
+    assert 0 not in ids and 1 not in ids
+    assert res.counters["bad_w"] == 1 and res.counters["nan_rays"] == octr["nan_rays"] == 1
+    keep = np.isin(want[4], [3, 4, 5, 6, 7])
+    got = res.frame.numpy()
+    assert np.array_equal(got[:, np.isin(got[4], [3, 4, 5, 6, 7])], want[:, keep])
+
+
+def test_argument_validation_returns_errors(cuda_device):
+    import ctypes
+
+    import torch
+
+    import pyrayt_b200
+    from pyrayt_b200 import _lib
+
+    scene, rays, _, gl = load_case("config1_collimator")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    d = torch.from_numpy(rays).cuda()
+    with pytest.raises(pyrayt_b200.PrtError, match="generation_limit"):
+        eng.trace(d, generation_limit=0)
+    with pytest.raises(pyrayt_b200.PrtError, match="65535"):
+        eng.trace(d, generation_limit=70000, record="none")
+    lib = _lib.load()
+    assert lib.prt_trace(None, None, None, 0, 0, None, None, None) == -1
+    assert b"null" in lib.prt_last_error()
+    out = ctypes.c_void_p()
+    assert lib.prt_scene_create(None, 0, ctypes.byref(out)) == -1
