@@ -176,6 +176,12 @@ class FlatScene:
         d.leaf_matp = ptr(self.leaf_matp, ctypes.c_double)
         return d
 
+    def fingerprint(self) -> bytes:
+        """Cheap identity of the flattened scene (all arrays, byte for byte)."""
+        return b"|".join(getattr(self, k).tobytes() for k in (
+            "comp_node_begin", "node_kind", "node_leaf", "node_aabb", "leaf_type", "leaf_obj", "leaf_param",
+            "leaf_nscale", "leaf_sid", "leaf_mat", "leaf_matp"))
+
     # ---- fixtures: scenes travel to the GPU box as JSON (floats via repr: exact round trip)
     def to_json(self) -> str:
         out = {}
