@@ -209,6 +209,10 @@ def test_drop_in_raytracer_api(torch_mod):
     det.move_x(1.0)
     df2 = tracer.trace()
     assert np.allclose(df2["x1"][df2["generation"] == 2], 4.0)
+    # extension: record only the rows that end on one surface
+    only = tracer.trace(record_surface=det)
+    full = tracer.trace()
+    assert np.array_equal(only.to_numpy(), full[full["surface"] == det.get_id()].to_numpy())
     # setters / getters
     tracer.set_rays_per_source(5)
     tracer.set_generation_limit(1)
