@@ -106,6 +106,29 @@ PRT_HD double div_by(double a, const Rcp& R) {
   return slow_div(a, R.b);                      // tiny, huge, inf, NaN or an unsafe denominator
 }
 
+// Two / three quotients by the same denominator: the 3-instruction form is computed for all of them
+// and one test decides whether any needs the guarded path (one branch instead of one per quotient).
+PRT_HD void div_by2(double a0, double a1, const Rcp& R, double& q0, double& q1) {
+  q0 = div_fast(a0, R);
+  q1 = div_fast(a1, R);
+  const bool ok = (exp_of(a0) - kExpLo < R.lim) & (exp_of(a1) - kExpLo < R.lim);
+  if (!ok) {
+    q0 = div_by(a0, R);
+    q1 = div_by(a1, R);
+  }
+}
+PRT_HD void div_by3(double a0, double a1, double a2, const Rcp& R, double& q0, double& q1, double& q2) {
+  q0 = div_fast(a0, R);
+  q1 = div_fast(a1, R);
+  q2 = div_fast(a2, R);
+  const bool ok = (exp_of(a0) - kExpLo < R.lim) & (exp_of(a1) - kExpLo < R.lim) & (exp_of(a2) - kExpLo < R.lim);
+  if (!ok) {
+    q0 = div_by(a0, R);
+    q1 = div_by(a1, R);
+    q2 = div_by(a2, R);
+  }
+}
+
 // per-generation reciprocals of a ray direction, shared by every bounding-box test against it
 struct RayInv {
   double r0, r1, r2;  // RN(1 / (d_k + z_k))
@@ -141,8 +164,8 @@ PRT_HD void clip_z(double s0, double s1, double zlo, double zhi, double oz, doub
                                        double b0_num, double& t0, double& t1) {
   const bool par = isz(dz);
   const Rcp den = make_rcp(dz + (par ? 1.0 : 0.0));
-  double b0 = div_by(b0_num, den);
-  double b1 = div_by(zhi - oz, den);
+  double b0, b1;
+  div_by2(b0_num, zhi - oz, den, b0, b1);
   if (par) {
     b0 = ((oz >= zlo) && (oz <= zhi)) ? -PRT_INF : PRT_INF;
     b1 = PRT_INF;
@@ -166,8 +189,8 @@ PRT_HD void cube_axis(double o, bool zf, const Rcp& den, double lo, double hi, d
     mx = PRT_INF;
     return;
   }
-  double h0 = div_by(-(o - lo), den);
-  double h1 = div_by(-(o - hi), den);
+  double h0, h1;
+  div_by2(-(o - lo), -(o - hi), den, h0, h1);
   sort2(h0, h1);
   mn = h0;
   mx = h1;
@@ -245,8 +268,8 @@ PRT_HD void plane_axis(double o, double d, double dim, double& mn, double& mx) {
   const bool zf = isz(d);
   const double half = dim / 2;
   const Rcp den = make_rcp(d + (zf ? 1.0 : 0.0));
-  double v0 = div_by(-(o - half), den);
-  double v1 = div_by(-(o + half), den);
+  double v0, v1;
+  div_by2(-(o - half), -(o + half), den, v0, v1);
   if (zf) {
     v0 = (fabs(o) <= half) ? -PRT_INF : PRT_INF;
     v1 = PRT_INF;
@@ -275,8 +298,7 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double disc = b * b - 4 * a * c;
       const double root = sqrt(fmax(0.0, disc));
       const Rcp den = make_rcp(2 * a);
-      t0 = div_by(-b + root, den);
-      t1 = div_by(-b - root, den);
+      div_by2(-b + root, -b - root, den, t0, t1);
       if (!(disc >= 0)) {
         t0 = PRT_INF;
         t1 = PRT_INF;
@@ -292,8 +314,8 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const bool lin = isz(a);
       const double root = sqrt(fmax(0.0, disc));
       const Rcp den = make_rcp(2 * a + (lin ? 1.0 : 0.0));
-      double s0 = div_by(-b + root, den);
-      double s1 = div_by(-b - root, den);
+      double s0, s1;
+      div_by2(-b + root, -b - root, den, s0, s1);
       if (!(disc >= 0)) {
         s0 = PRT_INF;
         s1 = PRT_INF;
@@ -319,8 +341,8 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const bool lin = isz(a);
       const double root = sqrt(fmax(0.0, disc));
       const Rcp den = make_rcp(2 * a + (lin ? 1.0 : 0.0));
-      double s0 = div_by(-b + root, den);
-      double s1 = div_by(-b - root, den);
+      double s0, s1;
+      div_by2(-b + root, -b - root, den, s0, s1);
       if (!(disc >= 0)) {
         s0 = PRT_INF;
         s1 = PRT_INF;
@@ -414,18 +436,17 @@ PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double&
   }
   if (!unit) {
     const Rcp nrm = make_rcp(sqrt(a0 * a0 + a1 * a1 + a2 * a2));
-    a0 = div_by(a0, nrm);
-    a1 = div_by(a1, nrm);
-    a2 = div_by(a2, nrm);
+    div_by3(a0, a1, a2, nrm, a0, a1, a2);
   }
   // M_obj^T n_obj, w dropped, normalise, flip (world_objects.py:411-418)
   double w0 = L.m[0] * a0 + L.m[4] * a1 + L.m[8] * a2;
   double w1 = L.m[1] * a0 + L.m[5] * a1 + L.m[9] * a2;
   double w2 = L.m[2] * a0 + L.m[6] * a1 + L.m[10] * a2;
   const Rcp wn = make_rcp(sqrt(w0 * w0 + w1 * w1 + w2 * w2));
-  n0 = div_by(w0, wn) * L.nscale;
-  n1 = div_by(w1, wn) * L.nscale;
-  n2 = div_by(w2, wn) * L.nscale;
+  div_by3(w0, w1, w2, wn, n0, n1, n2);
+  n0 *= L.nscale;
+  n1 *= L.nscale;
+  n2 *= L.nscale;
 }
 
 // ---------------------------------------------------------------- CSG hit lists
@@ -780,9 +801,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   o.n_next = r.nidx;
   // unit incoming direction: the row's tilt (:177) and refract()'s normalised vector (operations.py:125)
   const Rcp rvn = make_rcp(vn);
-  o.t0n = div_by(r.v0, rvn);
-  o.t1n = div_by(r.v1, rvn);
-  o.t2n = div_by(r.v2, rvn);
+  div_by3(r.v0, r.v1, r.v2, rvn, o.t0n, o.t1n, o.t2n);
   bool goes_on = true;
   if (L.mat == PRT_MAT_ABSORBER) {  // materials.py:47-50
     o.nv0 = 0;
@@ -835,9 +854,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
       o.nv2 = u2 + k * n2;
     }
     const Rcp nn = make_rcp(sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2));
-    o.nv0 = div_by(o.nv0, nn);
-    o.nv1 = div_by(o.nv1, nn);
-    o.nv2 = div_by(o.nv2, nn);
+    div_by3(o.nv0, o.nv1, o.nv2, nn, o.nv0, o.nv1, o.nv2);
   } else {
     c.w1 |= kCtrUntr;  // the reference raises AttributeError here
     return false;
