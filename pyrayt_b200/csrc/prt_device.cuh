@@ -38,8 +38,8 @@ namespace prt {
 PRT_HD bool isz(double x) { return fabs(x) <= 1e-8; }
 // np.isclose(p, v): |p - v| <= 1e-8 + 1e-5 |v|
 PRT_HD bool iscl(double p, double v) {
-  if (isinf(p) || isinf(v)) return p == v;
-  return fabs(p - v) <= (1e-8 + 1e-5 * fabs(v));
+  // equal infinities compare close in NumPy; inf - inf = NaN fails the first test, p == v catches it
+  return (fabs(p - v) <= (1e-8 + 1e-5 * fabs(v))) | (p == v);
 }
 PRT_HD void sort2(double& a, double& b) {
   if (b < a) {
@@ -197,7 +197,7 @@ PRT_HD void cube_axis(double o, bool zf, const Rcp& den, double lo, double hi, d
 }
 
 // a coordinate / span for which o - s is 0 or at least 2^-900 in magnitude
-PRT_HD bool tame(double x) { return x == 0.0 || (exp_of(x) - 200u < 1700u - 200u); }  // 0 or [2^-823, 2^677)
+PRT_HD bool tame(double x) { return (x == 0.0) | (exp_of(x) - 200u < 1700u - 200u); }  // 0 or [2^-823, 2^677)
 
 // reciprocals of the direction of a ray starting at (o0,o1,o2); `boxes_tame`: every box this
 // ray will be tested against has spans that are 0 or in [2^-823, 2^677) (BlobHeader.flags & 1)
@@ -211,8 +211,8 @@ PRT_HD RayInv make_ray_inv(double o0, double o1, double o2, double d0, double d1
   I.r2 = R2.r;
   // Fast slab form: differences of tame numbers are 0 or >= 2^-876 and < 2^678, denominators are in
   // [2^-66, 2^66) -> every quotient and its FMA residual stay normal, so div_fast is exact.
-  const bool den_ok = (exp_of(e0) - 957u < 132u) && (exp_of(e1) - 957u < 132u) && (exp_of(e2) - 957u < 132u);
-  const bool fast = boxes_tame && !z0 && !z1 && !z2 && den_ok && tame(o0) && tame(o1) && tame(o2);
+  const bool den_ok = (exp_of(e0) - 957u < 132u) & (exp_of(e1) - 957u < 132u) & (exp_of(e2) - 957u < 132u);
+  const bool fast = boxes_tame & !z0 & !z1 & !z2 & den_ok & tame(o0) & tame(o1) & tame(o2);
   I.bits = (z0 ? 1u : 0u) | (z1 ? 2u : 0u) | (z2 ? 4u : 0u) | (e0 < 0 ? 8u : 0u) | (e1 < 0 ? 16u : 0u) |
            (e2 < 0 ? 32u : 0u) | (fast ? 64u : 0u) | (R0.lim ? 128u : 0u) | (R1.lim ? 256u : 0u) |
            (R2.lim ? 512u : 0u);
@@ -363,7 +363,7 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const bool skew = isz(d2);
       double t = -o2 / (d2 + (skew ? 1.0 : 0.0));
       if (skew) t = PRT_INF;
-      if (!(t >= lo && t <= hi)) t = PRT_INF;
+      if (!((t >= lo) & (t <= hi))) t = PRT_INF;
       t0 = t;
       t1 = t;
     } break;
@@ -578,7 +578,7 @@ PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, d
 
 // array_csg's keep rule for an entry whose running count is `cnt` after and `prev` before it
 PRT_HD bool csg_keep(int op, int cnt, int prev) {
-  return (op == PRT_UNION) ? ((cnt != 0) != (prev != 0)) : (cnt == 2 || prev == 2);
+  return (op == PRT_UNION) ? ((cnt != 0) != (prev != 0)) : ((cnt == 2) | (prev == 2));
 }
 
 // merge of (a0,a1) [left] with (b0,b1) [right]; +inf marks a missing entry.  Outputs keep flags
@@ -587,20 +587,20 @@ PRT_HD void merge22(int op, double a0, double a1, double b0, double b1, bool kee
   const bool va0 = a0 < PRT_INF, va1 = a1 < PRT_INF, vb0 = b0 < PRT_INF, vb1 = b1 < PRT_INF;
   const bool l00 = b0 < a0, l01 = b0 < a1, l10 = b1 < a0, l11 = b1 < a1;  // l[j][i] = b_j < a_i
   const int rb0 = (int)l00 + (int)l10, rb1 = (int)l01 + (int)l11;
-  const int lb0 = (int)(va0 && !l00) + (int)(va1 && !l01), lb1 = (int)(va0 && !l10) + (int)(va1 && !l11);
-  if ((va0 && vb0 && a0 == b0) || (va0 && vb1 && a0 == b1) || (va1 && vb0 && a1 == b0) || (va1 && vb1 && a1 == b1))
-    tie = true;
+  const int lb0 = (int)(va0 & !l00) + (int)(va1 & !l01), lb1 = (int)(va0 & !l10) + (int)(va1 & !l11);
+  // (bitwise logic on purpose: no short-circuit branches)
+  tie |= (va0 & vb0 & (a0 == b0)) | (va0 & vb1 & (a0 == b1)) | (va1 & vb0 & (a1 == b0)) | (va1 & vb1 & (a1 == b1));
   const int start = (op == PRT_DIFFERENCE) ? 1 : 0;
   const int sR = (op == PRT_DIFFERENCE) ? -1 : 1;
   int cnt;
   cnt = start + 1 + sR * (rb0 & 1);                 // A0: first left entry (enters)
-  keep[0] = va0 && csg_keep(op, cnt, cnt - 1);
+  keep[0] = va0 & csg_keep(op, cnt, cnt - 1);
   cnt = start + 0 + sR * (rb1 & 1);                 // A1: second left entry (exits)
-  keep[1] = va1 && csg_keep(op, cnt, cnt + 1);
+  keep[1] = va1 & csg_keep(op, cnt, cnt + 1);
   cnt = start + (lb0 & 1) + sR;                     // B0
-  keep[2] = vb0 && csg_keep(op, cnt, cnt - sR);
+  keep[2] = vb0 & csg_keep(op, cnt, cnt - sR);
   cnt = start + (lb1 & 1);                          // B1
-  keep[3] = vb1 && csg_keep(op, cnt, cnt + sR);
+  keep[3] = vb1 & csg_keep(op, cnt, cnt + sR);
   pos[0] = rb0;
   pos[1] = 1 + rb1;
   pos[2] = lb0;
@@ -609,10 +609,9 @@ PRT_HD void merge22(int op, double a0, double a1, double b0, double b1, bool kee
 
 // running best of one component: first positive kept entry in merged order
 PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
-  if (keep && t > 0 && t < ct) {
-    ct = t;
-    cl = leaf;
-  }
+  const bool take = keep & (t > 0) & (t < ct);
+  ct = take ? t : ct;
+  cl = take ? leaf : cl;
 }
 
 // shapes 2/3: (A op1 B) [op2 C] with their bounding boxes (csg.py:118-160 for a left-deep tree)
@@ -625,7 +624,7 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
   cube_hits(C.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
   if (!(b0 < PRT_INF)) return;  // csg.py:126-133
   // proven-box pruning: a box behind the ray or beyond the best hit so far cannot matter
-  if ((C.flags & 1) && (b1 < -kCullMargin || b0 > best_t + kCullMargin)) return;
+  if (((C.flags & 1) != 0) & ((b1 < -kCullMargin) | (b0 > best_t + kCullMargin))) return;
   bool inner_hit = true;
   if (shape == SHAPE_LEFT3) {
     cube_hits(C.inner_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
@@ -676,18 +675,18 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
   for (int e = 0; e < 4; ++e) {
     const bool l0 = c0 < x[e], l1 = c1 < x[e];
     const int rb = (int)l0 + (int)l1;
-    lb0 += (int)(keep[e] && !l0);
-    lb1 += (int)(keep[e] && !l1);
-    if (keep[e] && ((vc0 && x[e] == c0) || (vc1 && x[e] == c1))) tie = true;
+    lb0 += (int)(keep[e] & !l0);
+    lb1 += (int)(keep[e] & !l1);
+    tie |= keep[e] & ((vc0 & (x[e] == c0)) | (vc1 & (x[e] == c1)));
     const int idx = popc32(km & ((1u << pos[e]) - 1u));
     const int up = (idx & 1) ? -1 : 1;  // even index enters
     const int cnt = start + ((idx + 1) & 1) + sR * (rb & 1);
-    keep2[e] = keep[e] && csg_keep(op2, cnt, cnt - up);
+    keep2[e] = keep[e] & csg_keep(op2, cnt, cnt - up);
   }
   int cnt = start + (lb0 & 1) + sR;
-  const bool kc0 = vc0 && csg_keep(op2, cnt, cnt - sR);
+  const bool kc0 = vc0 & csg_keep(op2, cnt, cnt - sR);
   cnt = start + (lb1 & 1);
-  const bool kc1 = vc1 && csg_keep(op2, cnt, cnt + sR);
+  const bool kc1 = vc1 & csg_keep(op2, cnt, cnt + sR);
   take_hit(keep2[0], a0, la, ct, cl);
   take_hit(keep2[1], a1, la, ct, cl);
   take_hit(keep2[2], q0, lb, ct, cl);
@@ -783,7 +782,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   o.row = false;
   const double vn = sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
   if (isz(vn)) return false;  // absorbed / zero direction (_pyrayt.py:415)
-  if (isnan(r.v0) || isnan(r.v1) || isnan(r.v2)) {
+  if (isnan(r.v0) | isnan(r.v1) | isnan(r.v2)) {
     c.w1 |= kCtrNan;  // every hit compares false in the reference -> miss
     return false;
   }
