@@ -376,6 +376,51 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
   }
 }
 
+// Two Sphere leaves at once (the two refracting surfaces of a lens): the same arithmetic as the
+// PRT_SPHERE case of leaf_hits, written side by side so that the two dependency chains (transform,
+// quadratic, square root, reciprocal, quotients) overlap in the pipeline instead of running one
+// after the other.
+PRT_HD void sphere_pair_hits(const Leaf& A, const Leaf& B, double p0, double p1, double p2, double v0, double v1,
+                             double v2, double& a0, double& a1, double& b0, double& b1) {
+  const double ao0 = A.m[0] * p0 + A.m[1] * p1 + A.m[2] * p2 + A.m[3];
+  const double bo0 = B.m[0] * p0 + B.m[1] * p1 + B.m[2] * p2 + B.m[3];
+  const double ao1 = A.m[4] * p0 + A.m[5] * p1 + A.m[6] * p2 + A.m[7];
+  const double bo1 = B.m[4] * p0 + B.m[5] * p1 + B.m[6] * p2 + B.m[7];
+  const double ao2 = A.m[8] * p0 + A.m[9] * p1 + A.m[10] * p2 + A.m[11];
+  const double bo2 = B.m[8] * p0 + B.m[9] * p1 + B.m[10] * p2 + B.m[11];
+  const double ad0 = A.m[0] * v0 + A.m[1] * v1 + A.m[2] * v2;
+  const double bd0 = B.m[0] * v0 + B.m[1] * v1 + B.m[2] * v2;
+  const double ad1 = A.m[4] * v0 + A.m[5] * v1 + A.m[6] * v2;
+  const double bd1 = B.m[4] * v0 + B.m[5] * v1 + B.m[6] * v2;
+  const double ad2 = A.m[8] * v0 + A.m[9] * v1 + A.m[10] * v2;
+  const double bd2 = B.m[8] * v0 + B.m[9] * v1 + B.m[10] * v2;
+  const double ra = A.prm[0], rb = B.prm[0];
+  const double aa = ad0 * ad0 + ad1 * ad1 + ad2 * ad2;
+  const double ba = bd0 * bd0 + bd1 * bd1 + bd2 * bd2;
+  const double ab = 2 * (ad0 * ao0 + ad1 * ao1 + ad2 * ao2);
+  const double bb = 2 * (bd0 * bo0 + bd1 * bo1 + bd2 * bo2);
+  const double ac = (ao0 * ao0 + ao1 * ao1 + ao2 * ao2) - ra * ra;
+  const double bc = (bo0 * bo0 + bo1 * bo1 + bo2 * bo2) - rb * rb;
+  const double adisc = ab * ab - 4 * aa * ac;
+  const double bdisc = bb * bb - 4 * ba * bc;
+  const double aroot = sqrt(fmax(0.0, adisc));
+  const double broot = sqrt(fmax(0.0, bdisc));
+  const Rcp aden = make_rcp(2 * aa);
+  const Rcp bden = make_rcp(2 * ba);
+  div_by2(-ab + aroot, -ab - aroot, aden, a0, a1);
+  div_by2(-bb + broot, -bb - broot, bden, b0, b1);
+  if (!(adisc >= 0)) {
+    a0 = PRT_INF;
+    a1 = PRT_INF;
+  }
+  if (!(bdisc >= 0)) {
+    b0 = PRT_INF;
+    b1 = PRT_INF;
+  }
+  sort2(a0, a1);
+  sort2(b0, b1);
+}
+
 // TracerSurface.get_world_normals (world_objects.py:401-418) with the primitives' normal()
 // (Sphere :273-296, Paraboloid :401-419, Plane :494-498, Cube :583-602, Cylinder :714-741)
 PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double& n0,
@@ -634,8 +679,24 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
   const int op1 = C.op1, op2 = C.op2;
   double a0 = PRT_INF, a1 = PRT_INF, q0 = PRT_INF, q1 = PRT_INF, c0 = PRT_INF, c1 = PRT_INF;
   // one (not unrolled) loop over the leaves keeps a single copy of leaf_hits in the hot loop
+  // Lenses carry two spherical surfaces ((aperture, sphere, sphere) for thick_lens, (sphere, sphere,
+  // aperture) for biconvex_lens): those two leaves are evaluated side by side (see sphere_pair_hits),
+  // the remaining leaf by the loop below.  `todo` = bit k set: leaf k still to be evaluated.
+  unsigned todo = inner_hit ? ((shape == SHAPE_LEFT3) ? 7u : 3u) : 4u;
+  if (inner_hit) {
+    const int ta = sc.leaves[la].type, tb = sc.leaves[lb].type;
+    const int tc = (shape == SHAPE_LEFT3) ? sc.leaves[lc].type : 0;
+    if ((tb == PRT_SPHERE) & (tc == PRT_SPHERE)) {
+      sphere_pair_hits(sc.leaves[lb], sc.leaves[lc], p0, p1, p2, v0, v1, v2, q0, q1, c0, c1);
+      todo = 1u;
+    } else if ((ta == PRT_SPHERE) & (tb == PRT_SPHERE)) {
+      sphere_pair_hits(sc.leaves[la], sc.leaves[lb], p0, p1, p2, v0, v1, v2, a0, a1, q0, q1);
+      todo &= 4u;
+    }
+  }
 #pragma unroll 1
-  for (int k = inner_hit ? 0 : 2; k < shape; ++k) {
+  for (int k = 0; k < 3; ++k) {
+    if (!((todo >> k) & 1u)) continue;
     const int lf = (k == 0) ? la : ((k == 1) ? lb : lc);
     double t0, t1;
     leaf_hits(sc.leaves[lf], p0, p1, p2, v0, v1, v2, t0, t1);
