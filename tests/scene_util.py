@@ -170,7 +170,10 @@ def random_scene_and_rays(seed, n_rays=512):
     bk7 = dict(mat=MAT_GLASS_SELLMEIER, matp=[1.03961212, 0.231792344, 1.01046945, 6.00069867e-3, 2.00179144e-2, 103.560653])
 
     def pose():
-        return translate(*rng.uniform(-3, 3, 3)) @ rot_z(rng.uniform(0, 360)) @ rot_y(rng.uniform(0, 360))
+        m = translate(*rng.uniform(-3, 3, 3)) @ rot_z(rng.uniform(0, 360)) @ rot_y(rng.uniform(0, 360))
+        if rng.random() < 0.4:  # non-uniform scale, like WorldObject.scale()
+            m = m @ np.diag(list(rng.uniform(0.6, 1.8, 3)) + [1.0])
+        return m
 
     def prim(kw):
         t = int(rng.integers(1, 6))
