@@ -139,7 +139,6 @@ struct RayInv {
 
 struct SceneView {
   const BlobHeader* h;
-  const int* comp;
   const Comp* comps;
   const Op* ops;
   const double* aabb;
@@ -149,7 +148,6 @@ struct SceneView {
 PRT_HD SceneView make_view(const unsigned char* blob) {
   SceneView s;
   s.h = reinterpret_cast<const BlobHeader*>(blob);
-  s.comp = reinterpret_cast<const int*>(blob + s.h->off_comp);
   s.comps = reinterpret_cast<const Comp*>(blob + s.h->off_comps);
   s.ops = reinterpret_cast<const Op*>(blob + s.h->off_ops);
   s.aabb = reinterpret_cast<const double*>(blob + s.h->off_aabb);

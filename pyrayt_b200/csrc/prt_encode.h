@@ -263,8 +263,6 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   }
   auto align8 = [](int x) { return (x + 7) & ~7; };
   int off = align8((int)sizeof(prt::BlobHeader));
-  h.off_comp = off;
-  off = align8(off + (int)sizeof(int) * (d->n_components + 1));
   h.off_comps = off;
   off = align8(off + (int)sizeof(prt::Comp) * (d->n_components > 0 ? d->n_components : 1));
   h.off_ops = off;
@@ -276,7 +274,6 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   h.total_bytes = off;
   blob.assign((size_t)off, 0);
   std::memcpy(blob.data(), &h, sizeof h);
-  std::memcpy(blob.data() + h.off_comp, comp_begin.data(), sizeof(int) * comp_begin.size());
   if (!comps.empty()) std::memcpy(blob.data() + h.off_comps, comps.data(), sizeof(prt::Comp) * comps.size());
   if (h.n_ops) std::memcpy(blob.data() + h.off_ops, enc.ops.data(), sizeof(prt::Op) * enc.ops.size());
   if (h.n_aabb) std::memcpy(blob.data() + h.off_aabb, enc.aabb.data(), sizeof(double) * enc.aabb.size());

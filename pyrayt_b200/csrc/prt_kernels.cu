@@ -1,8 +1,10 @@
 // pyrayt_b200 trace kernels for sm_100a (B200).
 //
-// K1 trace_kernel      one thread = one ray, every generation in a persistent loop
+// K1 trace_kernel<RECORD, GENERIC>
+//                      one thread = one ray, every generation in a persistent loop
 //                      (replaces RayTracer._st_propagate/_st_interact and everything under
-//                      them: pyrayt/_pyrayt.py:370-452).
+//                      them: pyrayt/_pyrayt.py:370-452).  GENERIC = false (all components bare
+//                      leaves or left-deep trees) compiles the CSG interpreter out.
 // K2 scan_runs_kernel / gen_offsets_kernel / gather_kernel
 //                      put the staged rows in the reference's (generation, id) order
 //                      (pyrayt/_pyrayt.py:186,:428-435).

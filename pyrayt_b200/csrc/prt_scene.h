@@ -1,10 +1,12 @@
 // Device-side scene encoding shared by the host ABI layer and the kernels.
 //
-// The caller hands prt_scene_create() postfix CSG programs (include/pyrayt_b200.h);
-// the kernels run a *preorder* program with skip targets so that the bounding-box
-// cull of CSGSurface.intersect (tinygfx/g3d/csg.py:126-133) can skip a whole
-// subtree per ray.  The encoded scene is one contiguous blob that every thread
-// block copies to shared memory once.
+// The caller hands prt_scene_create() postfix CSG programs (include/pyrayt_b200.h).
+// The encoder (prt_encode.h) turns each component into a Comp record: bare leaves and
+// left-deep trees of two or three leaves (everything the reference's factories build)
+// are evaluated in registers straight from that record; any other tree runs a *preorder*
+// op program with skip targets, so that the bounding-box cull of CSGSurface.intersect
+// (tinygfx/g3d/csg.py:126-133) can skip a whole subtree per ray.  The encoded scene is
+// one contiguous blob that every thread block copies to shared memory once.
 #pragma once
 #include <stdint.h>
 
@@ -69,7 +71,6 @@ struct Leaf {
 
 struct BlobHeader {
   int n_components, n_ops, n_leaves, n_aabb;
-  int off_comp;    // int[n_components+1] : op ranges per component
   int off_ops;     // Op[n_ops]
   int off_aabb;    // double[n_aabb*6]
   int off_leaves;  // Leaf[n_leaves]
