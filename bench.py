@@ -292,6 +292,10 @@ def main():
         if t.get("workload") == wl.name and t.get("rays") == n:
             roof["traffic"] = t.get("dram_bytes_per_launch")
             roof["traffic_source"] = t.get("source")
+            # what the counters say the pipe actually did (pruning answers tests without executing them,
+            # so the algorithmic fraction above can exceed it)
+            roof64["ncu_fp64_pipe_active_pct"] = t.get("fp64_pipe_active_pct")
+            roof64["ncu_issue_active_pct"] = t.get("issue_active_pct")
 
     # ------------------------------------------------------------------ end to end through host buffers
     e2e = None
