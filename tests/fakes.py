@@ -133,3 +133,25 @@ class ConeOfRays(_RefSource):
 
 class WedgeOfRays(_RefSource):
     _kind, _attr = 13, "_angle"
+
+
+class OrthographicCamera:
+    """Stand-in for tinygfx.g3d.OrthographicCamera (world_objects.py:499-537): rays along +x."""
+
+    def __init__(self, h_pixels, h_width, aspect, world=None):
+        self._h, self._w, self._vw, self._v = h_pixels, h_width, aspect * h_width, int(aspect * h_pixels)
+        self._world = np.eye(4) if world is None else np.asarray(world, dtype=float)
+
+    def get_resolution(self):
+        return (self._h, self._v)
+
+    def generate_rays(self):
+        hs = np.linspace(self._w / 2, -self._w / 2, self._h)
+        vs = np.linspace(self._vw / 2, -self._vw / 2, self._v)
+        rays = np.zeros((2, 4, self._h * self._v))
+        rays[0, 3] = 1
+        ys, zs = np.meshgrid(hs, vs)
+        rays[0, 1], rays[0, 2], rays[1, 0] = ys.reshape(-1), zs.reshape(-1), 1
+        rays = np.matmul(self._world, rays)
+        rays[1] /= np.linalg.norm(rays[1], axis=0)
+        return rays

@@ -254,3 +254,24 @@ def test_nearest_hit_and_scene_update(torch_mod):
         got = eng.trace(torch_mod.from_numpy(rays).cuda(), generation_limit=12, to_host=True).frame.numpy()
         want, _ = oracle.trace(s2, rays, 12)
         assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_camera_nearest_image_matches_oracle(torch_mod):
+    """N3: the renderers' per-pixel nearest-hit loop (tinygfx/g3d/renderers.py:72-94) as one kernel."""
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import fakes, scene_util as su
+
+    glass = fakes.BasicRefractor(1.5)
+    lens = fakes.CSG(fakes.Surface(fakes.Sphere(2.0), glass, su.translate(1.9, 0, 0)),
+                     fakes.Surface(fakes.Sphere(2.0), glass, su.translate(-1.9, 0, 0)), 2, (-0.1, 0.1, -1, 1, -1, 1))
+    ball = fakes.Surface(fakes.Sphere(0.3), fakes._ReflectingMaterial(), su.translate(1.0, 0.5, 0.2))
+    cam = fakes.OrthographicCamera(96, 2.4, 0.75, world=su.translate(-5, 0, 0))
+    img = pyrayt_b200.render.camera_nearest(cam, [lens, ball])
+    assert img["distance"].shape == img["surface"].shape == (72, 96) and img["normal"].shape == (72, 96, 3)
+    t, sid, nrm = oracle.nearest(pyrayt_b200.flatten([lens, ball]), cam.generate_rays())
+    assert np.array_equal(img["distance"].ravel(), t) and np.array_equal(img["surface"].ravel(), sid)
+    assert np.array_equal(np.moveaxis(img["normal"], -1, 0).reshape(3, -1), nrm, equal_nan=True)
+    assert {-1, ball.get_id(), lens._l_child.get_id()} <= set(np.unique(sid).tolist())
+    canvas = pyrayt_b200.render.edge_canvas(img["surface"])
+    assert canvas.shape == (72, 96, 4) and 0 < canvas[..., 3].mean() < 0.5
