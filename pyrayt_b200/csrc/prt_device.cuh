@@ -760,13 +760,14 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
 // bare leaves or left-deep (every reference factory) run a smaller kernel with no lists in memory.
 template <bool GENERIC>
 PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0, double v1, double v2,
-                        HitStack* S, double& best_t, int& best_leaf, bool& tie) {
+                        int skip, HitStack* S, double& best_t, int& best_leaf, bool& tie) {
   best_t = PRT_INF;
   best_leaf = -1;
   const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
   const int nc = sc.h->n_components;
   {
     for (int c = 0; c < nc; ++c) {
+      if (c == skip) continue;  // convex solid the ray left in the previous generation
       const Comp& C = sc.comps[c];
       const int shape = C.shape;
       if (shape == SHAPE_LEAF) {  // bare TracerSurface component: no list needed
@@ -814,6 +815,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
 
 struct RayState {
   double p0, p1, p2, v0, v1, v2, wl, nidx;  // generation / intensity / id are only copied to the rows
+  int skip;  // component the ray has just left for good (convex solid, see Comp.flags bit 1), or -1
 };
 
 struct StepOut {
@@ -823,6 +825,7 @@ struct StepOut {
   double t0n, t1n, t2n;      // unit tilt of the incoming direction
   double nv0, nv1, nv2;      // direction after the interaction
   double n_next;             // refractive index after the interaction
+  int skip;                  // component that cannot be hit in the next generation, or -1
 };
 
 // per-ray event counters packed into two words (they stay live for the whole kernel):
@@ -835,6 +838,15 @@ constexpr unsigned kCtrTie = 1u << 16, kCtrUntr = 1u << 17, kCtrNan = 1u << 18, 
 
 // _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
 // returns true when the ray goes on to generation g+1.
+// A ray that leaves a convex solid through one of its faces (its new direction has a clearly positive
+// component along the outward normal there) cannot hit that solid again until it changes direction:
+// the whole solid lies behind the tangent plane.  Returns that component for the next generation's
+// nearest-hit search to skip, else -1.  (`out_dot` = new direction . outward unit normal; the
+// threshold keeps grazing exits, where rounding could matter, on the ordinary path.)
+PRT_HD int leaves_for_good(const SceneView& sc, const Leaf& L, double out_dot) {
+  return ((L.comp >= 0) && (out_dot > 1e-3) && (sc.comps[L.comp].flags & 2)) ? L.comp : -1;
+}
+
 template <bool GENERIC>
 PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int generation_limit, HitStack* S,
                        StepOut& o, StepCounters& c) {
@@ -849,7 +861,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   double best_t;
   int best_leaf;
   bool tie = false;
-  nearest_hit<GENERIC>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, S, best_t, best_leaf, tie);
+  nearest_hit<GENERIC>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, r.skip, S, best_t, best_leaf, tie);
   if (tie) c.w1 |= kCtrTie;
   if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
   const Leaf& L = sc.leaves[best_leaf];
@@ -857,6 +869,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   o.e1 = r.p1 + r.v1 * best_t;
   o.e2 = r.p2 + r.v2 * best_t;
   o.n_next = r.nidx;
+  o.skip = -1;
   // unit incoming direction: the row's tilt (:177) and refract()'s normalised vector (operations.py:125)
   const Rcp rvn = make_rcp(vn);
   div_by3(r.v0, r.v1, r.v2, rvn, o.t0n, o.t1n, o.t2n);
@@ -875,6 +888,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
     o.nv0 = r.v0 - 2 * n0 * dots;
     o.nv1 = r.v1 - 2 * n1 * dots;
     o.nv2 = r.v2 - 2 * n2 * dots;
+    o.skip = leaves_for_good(sc, L, o.nv0 * n0 + o.nv1 * n1 + o.nv2 * n2);
   } else if (L.mat == PRT_MAT_GLASS_CONST || L.mat == PRT_MAT_GLASS_SELLMEIER) {
     // materials.py:70-75,:112-118,:136-145 ; operations.py:110-162
     double n0, n1, n2;
@@ -913,6 +927,9 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
     }
     const Rcp nn = make_rcp(sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2));
     div_by3(o.nv0, o.nv1, o.nv2, nn, o.nv0, o.nv1, o.nv2);
+    // when exiting, n0..n2 were flipped above and now hold minus the outward normal: a refracted ray
+    // has a positive outward component, a totally reflected one a negative one
+    o.skip = leaves_for_good(sc, L, exiting ? -(o.nv0 * n0 + o.nv1 * n1 + o.nv2 * n2) : -1.0);
   } else {
     c.w1 |= kCtrUntr;  // the reference raises AttributeError here
     return false;
@@ -930,6 +947,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
 // generation g -> g+1 (pyrayt/_pyrayt.py:436-449)
 PRT_HD void advance_ray(RayState& r, const StepOut& o, int g, double ray_offset) {
   (void)g;
+  r.skip = o.skip;
   r.nidx = o.n_next;
   r.v0 = o.nv0;
   r.v1 = o.nv1;

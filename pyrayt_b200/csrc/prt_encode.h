@@ -222,6 +222,14 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
         for (int k = 0; k < 6; ++k) C.root_box[k] = enc.aabb[6 * o[0].a + k];
         for (int k = 0; k < 6; ++k) C.inner_box[k] = enc.aabb[6 * o[1].a + k];
       }
+      // convex solids: intersections of convex primitives (every leaf type but the flat Plane)
+      if (shape == prt::SHAPE_LEFT2 || shape == prt::SHAPE_LEFT3) {
+        bool convex = C.op1 == PRT_INTERSECT && (shape == prt::SHAPE_LEFT2 || C.op2 == PRT_INTERSECT);
+        const int lv[3] = {C.leaf_a, C.leaf_b, C.leaf_c};
+        for (int k = 0; k < (shape == prt::SHAPE_LEFT3 ? 3 : 2); ++k)
+          if (d->leaf_type[lv[k]] == PRT_PLANE || d->leaf_nscale[lv[k]] != 1.0) convex = false;
+        if (convex) C.flags |= 2;
+      }
       comps.push_back(C);
     }
     if (enc.tree[root].kind != PRT_LEAF && enc.root_box_is_bound(root)) {
@@ -287,8 +295,13 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
     L.sid = (double)d->leaf_sid[l];
     L.type = d->leaf_type[l];
     L.mat = d->leaf_mat[l];
+    L.comp = -1;
+    L.pad = 0;
   }
 
+  for (int c = 0; c < d->n_components; ++c)
+    for (int nd = d->comp_node_begin[c]; nd < d->comp_node_begin[c + 1]; ++nd)
+      if (d->node_kind[nd] == PRT_LEAF) leaves[d->node_leaf[nd]].comp = c;
   return PRT_OK;
 }
 

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
-  RayState rs = {0, 0, 0, 0, 0, 0, 0, 1};
+  RayState rs = {0, 0, 0, 0, 0, 0, 0, 1, -1};
   StepCounters sc_ctr = {0, 0};
   unsigned c_drop = 0, c_badw = 0;
   if (valid) {
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) nearest_kernel(cons
   double best_t;
   int best_leaf;
   bool tie = false;
-  nearest_hit<true>(sc, p0, p1, p2, v0, v1, v2, &S, best_t, best_leaf, tie);
+  nearest_hit<true>(sc, p0, p1, p2, v0, v1, v2, -1, &S, best_t, best_leaf, tie);
   t_out[i] = best_t;
   sid_out[i] = best_leaf >= 0 ? (long long)sc.leaves[best_leaf].sid : -1;
   if (normals) {

@@ -47,6 +47,8 @@ enum Shape : int {
 struct Comp {
   int shape;   // Shape
   int flags;   // bit 0: the root box provably contains the solid -> pruning allowed
+               // bit 1: the solid is convex (INTERSECT of convex primitives): a ray that has just left
+               //        it through one of its faces cannot hit it again before it changes direction
   int begin, end;                  // ops [begin, end)
   int leaf_a, leaf_b, leaf_c;      // SHAPE_LEAF: leaf_a; SHAPE_LEFT2: a, b; SHAPE_LEFT3: a, b, c
   int op1, op2;                    // (A op1 B) op2 C
@@ -67,6 +69,8 @@ struct Leaf {
   double sid;      // surface id as it appears in the frame (float64 column)
   int type;        // prt_prim
   int mat;         // prt_material
+  int comp;        // component this leaf belongs to
+  int pad;
 };
 
 struct BlobHeader {

@@ -32,6 +32,7 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   unsigned long long tie_rays = 0, gens = 0, segs = 0, untr = 0, nans = 0, lims = 0;
   for (long long i = 0; i < n; ++i) {
     prt::RayState r;
+    r.skip = -1;
     r.p0 = rays[0 * stride + i]; r.p1 = rays[1 * stride + i]; r.p2 = rays[2 * stride + i];
     r.v0 = rays[4 * stride + i]; r.v1 = rays[5 * stride + i]; r.v2 = rays[6 * stride + i];
     const double gen0 = rays[8 * stride + i], inten = rays[9 * stride + i], id = rays[12 * stride + i];
