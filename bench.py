@@ -297,6 +297,25 @@ def main():
             roof64["ncu_fp64_pipe_active_pct"] = t.get("fp64_pipe_active_pct")
             roof64["ncu_issue_active_pct"] = t.get("issue_active_pct")
 
+    # ------------------------------------------------------------------ read-out on the device frame (N2)
+    # outside the timed steps: what a user reads off the frame (per-field spot on the detector) without
+    # copying the frame to the host; all-reduced over the ranks between its two passes
+    from pyrayt_b200 import analytics
+
+    det = float(scene.leaf_sid[-1])
+    per_group = (world * n + 8) // 9
+    analytics.spot_stats(res, per_group, 9, surface=det)
+    r0, r1 = ev(), ev()
+    r0.record()
+    spot = analytics.spot_stats(res, per_group, 9, surface=det)
+    r1.record()
+    r1.synchronize()
+    readout = {"what": "analytics.spot_stats: 9 ray-index groups, rows ending on the detector, two passes "
+                       "(prt_spot_moments x2 + prt_spot_centers) incl. the small D2H of the table",
+               "ms": max_over_ranks(r0.elapsed_time(r1)), "rows_scanned_per_gpu": rows,
+               "detector_rows": int(spot["n"].sum()), "rms_radius_group0": float(spot["rms_radius"][0]),
+               "frame_bytes_left_on_device_per_gpu": rows * 120}
+
     # ------------------------------------------------------------------ end to end through host buffers
     e2e = None
     res = None  # drop the device frame of the last resident step before the host-buffer run
@@ -323,7 +342,7 @@ def main():
                        "generation_limit": G, "leaves": scene.n_leaves, "rows_per_ray": rows / n,
                        "parallelism": f"ray-range x{world}", "numa_node_rank0": numa_node, "l2": "inputs larger than L2 (rays + staging >> 126 MB)"},
             "ray_surface_tests_per_s": tests_per_s, "segments_per_s": world * rows / (ms_per_step * 1e-3),
-            "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e, "readout": readout,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "counters": {k: counters[k] for k in ("rays", "generations", "segments", "tie_rays", "rows_dropped")},
         }

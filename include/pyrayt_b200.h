@@ -244,6 +244,55 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
                         int64_t first_index, void* cuda_stream);
 
 /*
+ * On-device read-out of a results frame: the pandas reductions of
+ * examples/lens_design.ipynb cells 11-20 run where the frame already is.  d_frame is the
+ * column-major frame prt_gather_frame wrote (column c of row r at d_frame[c*frame_stride + r]).
+ *
+ * Row selection (the notebook's two filters): PRT_SELECT_SURFACE keeps rows with
+ * surface == value (`results['surface'] == imager.get_id()`, cells 11/19/38), PRT_SELECT_GENERATION
+ * rows with generation == value (`results['generation'] == max`, cells 12/15/20).
+ */
+enum prt_select { PRT_SELECT_ALL = 0, PRT_SELECT_SURFACE = 1, PRT_SELECT_GENERATION = 2 };
+#define PRT_SPOT_COLS 16
+#define PRT_SPOT_CENTER_COLS 4
+#define PRT_SPOT_MAX_GROUPS 256
+
+/*
+ * Per-group moments of the selected rows; group = floor(id / rays_per_group), the reference's
+ * source_id (RayTracer.calculate_source_ids, pyrayt/_pyrayt.py:316-327); rows whose group is
+ * >= n_groups are ignored.  d_center (optional, may be NULL = all zero): per group
+ * {cy, cz, cf, ct}; sums are taken of (value - centre) so a second call with the centroids of the
+ * first gives cancellation-free second moments.  d_out: n_groups x PRT_SPOT_COLS doubles,
+ *   0 n            1 S(y1-cy)      2 S(z1-cz)      3 S(y1-cy)^2    4 S(z1-cz)^2   5 S(y1-cy)(z1-cz)
+ *   6 min y1       7 max y1        8 min z1        9 max z1
+ *  10 n_f (rows with a finite focus)   11 S(f-cf)   12 S(f-cf)^2,  f = -x_tilt*y0/y_tilt + x0 (cell 12)
+ *  13 S(y_tilt-ct) 14 S(y_tilt-ct)^2  15 S(sin(y_tilt)-ct)^2 (the coma metric of cell 20, ct = sin(angle))
+ * Sums are accumulated with floating-point atomics: the order, hence the last bits, may differ
+ * between calls.  `blocks` > 0 caps the grid (default: one block per 8192 rows).
+ */
+int prt_spot_moments(const double* d_frame, int64_t rows, int64_t frame_stride, int32_t select, double value,
+                     int64_t rays_per_group, int32_t n_groups, const double* d_center, double* d_out,
+                     int32_t blocks, void* cuda_stream);
+
+/* centres for a second, centred prt_spot_moments call: d_center_out = d_center_in (or 0) + mean residual of d_sums */
+int prt_spot_centers(const double* d_sums, const double* d_center_in, int32_t n_groups, double* d_center_out,
+                     void* cuda_stream);
+
+/*
+ * The focus table of cells 12 and 15: one column per selected row, in frame order, rows
+ * {id, radius, focus, wavelength}: radius = y0 of the ray's generation-0 row (the first gen0_rows
+ * rows of the frame, ids first_id .. first_id + gen0_rows - 1 in order; NaN if absent),
+ * focus = -x_tilt*y0/y_tilt + x0.  Row k of output column j at d_table[k*table_stride + j]; at most
+ * table_capacity columns are written.  Workspace: d_block_count / d_block_base hold
+ * prt_axis_table_blocks(rows) entries; d_total[1] receives the number of selected rows (d_total[0] = 0).
+ */
+int64_t prt_axis_table_blocks(int64_t rows);
+int prt_axis_table(const double* d_frame, int64_t rows, int64_t frame_stride, int32_t select, double value,
+                   int64_t first_id, int64_t gen0_rows, int32_t* d_block_count, int64_t* d_block_base,
+                   int64_t* d_total, double* d_table, int64_t table_stride, int64_t table_capacity,
+                   void* cuda_stream);
+
+/*
  * Measurement aid (no reference counterpart): launches `blocks` x 256 threads that each run
  * `iters` x 8 independent double-precision FMAs, so the caller can time the FP64 pipe's
  * FMA rate with CUDA events (flops = blocks*256*iters*16).  d_scratch: >= 1 double.

@@ -9,9 +9,9 @@ from ._lib import FRAME_COLUMNS, PrtError, load as load_library
 from .scene import FlatScene, SceneError, flatten
 from .engine import Engine, TraceResult
 from .tracer import RayTracer, UntraceableSurfaceError, install
-from . import render, sources
+from . import analytics, render, sources
 
 __all__ = [
     "RayTracer", "Engine", "TraceResult", "FlatScene", "flatten", "SceneError", "PrtError",
-    "UntraceableSurfaceError", "install", "sources", "render", "FRAME_COLUMNS", "load_library",
+    "UntraceableSurfaceError", "install", "sources", "render", "analytics", "FRAME_COLUMNS", "load_library",
 ]

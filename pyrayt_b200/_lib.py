@@ -16,6 +16,8 @@ ABI_VERSION = 1
 FRAME_COLS = 15
 RAY_ROWS = 13
 RECORD_ALL, RECORD_SURFACE, RECORD_NONE = 0, 1, 2
+SELECT_ALL, SELECT_SURFACE, SELECT_GENERATION = 0, 1, 2
+SPOT_COLS, SPOT_CENTER_COLS, SPOT_MAX_GROUPS = 16, 4, 256
 
 FRAME_COLUMNS = (
     "generation", "intensity", "wavelength", "index", "id", "surface",
@@ -33,6 +35,7 @@ EXPORTS = (
     "prt_abi_version", "prt_last_error", "prt_tile_rays", "prt_scene_create", "prt_scene_destroy",
     "prt_scene_n_leaves", "prt_trace", "prt_scan_runs", "prt_gather_frame", "prt_intersect",
     "prt_generate_source", "prt_fp64_probe", "prt_nearest_hit", "prt_scene_update",
+    "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
 )
 
 
@@ -110,6 +113,15 @@ def load():
     lib.prt_nearest_hit.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.prt_scene_update.restype = ctypes.c_int
     lib.prt_scene_update.argtypes = [vp, vp, vp]
+    f64 = ctypes.c_double
+    lib.prt_spot_moments.restype = ctypes.c_int
+    lib.prt_spot_moments.argtypes = [vp, i64, i64, i32, f64, i64, i32, vp, vp, i32, vp]
+    lib.prt_spot_centers.restype = ctypes.c_int
+    lib.prt_spot_centers.argtypes = [vp, vp, i32, vp, vp]
+    lib.prt_axis_table_blocks.restype = i64
+    lib.prt_axis_table_blocks.argtypes = [i64]
+    lib.prt_axis_table.restype = ctypes.c_int
+    lib.prt_axis_table.argtypes = [vp, i64, i64, i32, f64, i64, i64, vp, vp, vp, vp, i64, i64, vp]
     lib.prt_fp64_probe.restype = ctypes.c_int
     lib.prt_fp64_probe.argtypes = [vp, i32, i32, vp]
     if lib.prt_abi_version() != ABI_VERSION:

@@ -26,6 +26,15 @@ cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int 
 cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
                               long long first, cudaStream_t st);
 cudaError_t prt_launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);
+cudaError_t prt_launch_spot_moments(const double* frame, long long rows, long long stride, int select, double value,
+                                    long long rays_per_group, int n_groups, const double* center, double* out,
+                                    int blocks, cudaStream_t st);
+cudaError_t prt_launch_spot_centers(const double* sums, const double* center_in, int n_groups, double* center_out,
+                                    cudaStream_t st);
+cudaError_t prt_launch_axis_table(const double* frame, long long rows, long long stride, int select, double value,
+                                  long long first_id, long long gen0_rows, int* block_count, long long* block_base,
+                                  long long* total, double* table, long long table_stride, long long table_capacity,
+                                  cudaStream_t st);
 cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const double* rays, long long n, double* t_out,
                                long long* sid_out, double* normals, cudaStream_t st);
 }
@@ -240,6 +249,53 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
   if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
   cudaError_t e = prt_launch_source(src, d_rays, n_rays, ray_stride, first_index, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "source kernel launch");
+  return PRT_OK;
+}
+
+static bool bad_select(int32_t select) { return select < PRT_SELECT_ALL || select > PRT_SELECT_GENERATION; }
+
+int prt_spot_moments(const double* d_frame, int64_t rows, int64_t frame_stride, int32_t select, double value,
+                     int64_t rays_per_group, int32_t n_groups, const double* d_center, double* d_out,
+                     int32_t blocks, void* cuda_stream) {
+  if (rows < 0 || (rows > 0 && !d_frame) || frame_stride < rows) return fail(PRT_ERR_INVALID, "bad frame");
+  if (!d_out) return fail(PRT_ERR_INVALID, "d_out is NULL");
+  if (bad_select(select)) return fail(PRT_ERR_INVALID, "unknown row selection");
+  if (n_groups < 1 || n_groups > PRT_SPOT_MAX_GROUPS)
+    return fail(PRT_ERR_INVALID, "n_groups must be 1.." + std::to_string(PRT_SPOT_MAX_GROUPS));
+  if (rays_per_group < 1) return fail(PRT_ERR_INVALID, "rays_per_group must be >= 1");
+  cudaError_t e = prt_launch_spot_moments(d_frame, rows, frame_stride, select, value, rays_per_group, n_groups,
+                                          d_center, d_out, blocks, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "spot moments launch");
+  return PRT_OK;
+}
+
+int prt_spot_centers(const double* d_sums, const double* d_center_in, int32_t n_groups, double* d_center_out,
+                     void* cuda_stream) {
+  if (!d_sums || !d_center_out) return fail(PRT_ERR_INVALID, "NULL buffer");
+  if (n_groups < 1 || n_groups > PRT_SPOT_MAX_GROUPS) return fail(PRT_ERR_INVALID, "bad n_groups");
+  cudaError_t e = prt_launch_spot_centers(d_sums, d_center_in, n_groups, d_center_out, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "spot centers launch");
+  return PRT_OK;
+}
+
+int64_t prt_axis_table_blocks(int64_t rows) { return rows <= 0 ? 0 : (rows + 1023) / 1024; }
+
+int prt_axis_table(const double* d_frame, int64_t rows, int64_t frame_stride, int32_t select, double value,
+                   int64_t first_id, int64_t gen0_rows, int32_t* d_block_count, int64_t* d_block_base,
+                   int64_t* d_total, double* d_table, int64_t table_stride, int64_t table_capacity,
+                   void* cuda_stream) {
+  if (rows < 0 || (rows > 0 && !d_frame) || frame_stride < rows) return fail(PRT_ERR_INVALID, "bad frame");
+  if (bad_select(select)) return fail(PRT_ERR_INVALID, "unknown row selection");
+  if (!d_total) return fail(PRT_ERR_INVALID, "d_total is NULL");
+  if (rows > 0 && (!d_block_count || !d_block_base)) return fail(PRT_ERR_INVALID, "workspace is NULL");
+  if (table_capacity < 0 || (table_capacity > 0 && !d_table) || table_stride < table_capacity)
+    return fail(PRT_ERR_INVALID, "bad table");
+  if (gen0_rows < 0 || gen0_rows > rows) return fail(PRT_ERR_INVALID, "gen0_rows out of range");
+  if (prt_axis_table_blocks(rows) > 0x7fffffffLL) return fail(PRT_ERR_INVALID, "frame too long for one call");
+  cudaError_t e = prt_launch_axis_table(d_frame, rows, frame_stride, select, value, first_id, gen0_rows,
+                                        d_block_count, (long long*)d_block_base, (long long*)d_total, d_table,
+                                        table_stride, table_capacity, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "axis table launch");
   return PRT_OK;
 }
 

@@ -85,25 +85,33 @@ def gather_rows(local_rows, device=None):
     return [o[:, : int(kk.item())] for o, kk in zip(outs, ks)]
 
 
-def detector_summary(frame, detector_sid: int, device=None) -> Optional[dict]:
-    """All-reduced spot statistics of the rows that ended on `detector_sid`: count, centroid, RMS radius."""
-    import torch
+def reduce_spot_sums(sums) -> None:
+    """Combine per-rank moment tables (n_groups, 16) of prt_spot_moments in place: the sums add,
+    columns 6..9 (min / max of y1, z1) take the min / max.  No-op without a process group."""
     import torch.distributed as dist
 
-    f = frame if isinstance(frame, torch.Tensor) else torch.as_tensor(frame)
-    m = f[5] == float(detector_sid)
-    y, z = f[10][m], f[11][m]
-    acc = torch.stack([m.sum().to(torch.float64), y.sum(), z.sum(), (y * y).sum(), (z * z).sum()])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        if device is not None:
-            acc = acc.to(device)
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-    acc = acc.cpu().numpy()
-    if acc[0] == 0:
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    lo = sums[:, [6, 8]].contiguous()
+    hi = sums[:, [7, 9]].contiguous()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    sums[:, [6, 8]] = lo
+    sums[:, [7, 9]] = hi
+
+
+def detector_summary(frame, detector_sid: int, device=None) -> Optional[dict]:
+    """Spot statistics of the rows that ended on `detector_sid`, over the ray sets of every rank:
+    count, centroid, RMS radius (the moment kernels of analytics.py, all-reduced between their passes)."""
+    from . import analytics
+
+    st = analytics.spot_stats(frame, rays_per_group=1 << 62, n_groups=1, surface=float(detector_sid))
+    n = int(st.loc[0, "n"])
+    if n == 0:
         return {"count": 0}
-    cy, cz = acc[1] / acc[0], acc[2] / acc[0]
-    rms = float(np.sqrt(max(0.0, acc[3] / acc[0] - cy * cy + acc[4] / acc[0] - cz * cz)))
-    return {"count": int(acc[0]), "centroid": (float(cy), float(cz)), "rms_radius": rms}
+    return {"count": n, "centroid": (float(st.loc[0, "y_mean"]), float(st.loc[0, "z_mean"])),
+            "rms_radius": float(st.loc[0, "rms_radius"])}
 
 
 def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:

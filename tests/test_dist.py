@@ -43,7 +43,13 @@ def _worker(rank, world, port, out):
         all_counts = pdist.exchange_counts(gen_counts)                       # C1
         det = int(scene.leaf_sid[-1])
         parts = pdist.gather_rows(torch.from_numpy(np.ascontiguousarray(frame[:, frame[5] == det])))  # C2
-        summary = pdist.detector_summary(frame, det)
+        # per-rank moment table as prt_spot_moments lays it out (count, sums, min / max of y1, z1)
+        hit = frame[:, frame[5] == det]
+        sums = torch.zeros((1, 16), dtype=torch.float64)
+        sums[0, 0], sums[0, 1], sums[0, 2] = hit.shape[1], hit[10].sum(), hit[11].sum()
+        sums[0, 6], sums[0, 7] = hit[10].min(initial=np.inf), hit[10].max(initial=-np.inf)
+        sums[0, 8], sums[0, 9] = hit[11].min(initial=np.inf), hit[11].max(initial=-np.inf)
+        pdist.reduce_spot_sums(sums)
         frames = pdist.gather_rows(torch.from_numpy(frame))
         if rank == 0:
             whole, _ = oracle.trace(scene, rays, gl)
@@ -52,7 +58,10 @@ def _worker(rank, world, port, out):
             want_det = whole[:, whole[5] == det]
             order = np.lexsort((det_rows[4], det_rows[0]))
             out.put((bool(np.array_equal(glob, whole)), bool(np.array_equal(det_rows[:, order], want_det)),
-                     summary["count"] == want_det.shape[1], all_counts.shape))
+                     int(sums[0, 0]) == want_det.shape[1] and float(sums[0, 6]) == want_det[10].min()
+                     and float(sums[0, 9]) == want_det[11].max()
+                     and abs(float(sums[0, 1]) - want_det[10].sum()) <= 1e-9 * max(1.0, np.abs(want_det[10]).sum()),
+                     all_counts.shape))
     finally:
         dist.destroy_process_group()
 
