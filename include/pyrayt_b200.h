@@ -219,6 +219,15 @@ int prt_nearest_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d
                     double* d_normals, void* cuda_stream);
 
 /*
+ * EdgeRender._st_propagate / ShadedRenderer._st_propagate (tinygfx/g3d/renderers.py:72-94,:188-210) exactly:
+ * the loop of prt_nearest_hit, except that -- like the renderers -- distance and surface are read from the
+ * unfiltered hit array at the argmin of the filtered one, so a pixel whose component hits are all behind
+ * the camera reports the component's first (negative) hit instead of a miss.  Same arguments.
+ */
+int prt_render_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d_t, int64_t* d_sid,
+                   double* d_normals, void* cuda_stream);
+
+/*
  * Re-encode a scene into an existing handle (same device buffer when the encoded size is unchanged):
  * for optimisation loops that move components or change radii between thousands of small traces
  * (examples/lens_design.ipynb cells 28-33).  The copy is enqueued on cuda_stream.

@@ -160,7 +160,13 @@ def world_normal(scene, leaf: int, point):
     return out
 
 
-def nearest(scene, rays: np.ndarray):
+def render_hit(scene, rays: np.ndarray):
+    """EdgeRender / ShadedRenderer._st_propagate (tinygfx/g3d/renderers.py:72-94): like nearest(), but a
+    pixel with no positive hit reports slot 0 of the unfiltered hit array (possibly a negative distance)."""
+    return nearest(scene, rays, _entry="prt_oracle_render_hit")
+
+
+def nearest(scene, rays: np.ndarray, _entry="prt_oracle_nearest"):
     """_st_propagate alone: rays (2,4,N) -> (distance (N,), surface id (N,), world normals (3,N))."""
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(8, -1)
     n = rays.shape[1]
@@ -169,8 +175,9 @@ def nearest(scene, rays: np.ndarray):
     nrm = np.empty((3, n))
     desc = scene.as_desc()
     L = lib()
-    L.prt_oracle_nearest.restype = ctypes.c_int
-    rc = L.prt_oracle_nearest(ctypes.byref(desc), _p(rays), ctypes.c_int64(n), _p(t),
+    fn = getattr(L, _entry)
+    fn.restype = ctypes.c_int
+    rc = fn(ctypes.byref(desc), _p(rays), ctypes.c_int64(n), _p(t),
                               sid.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _p(nrm))
     if rc:
         raise RuntimeError("oracle nearest failed")

@@ -35,7 +35,7 @@ EXPORTS = (
     "prt_abi_version", "prt_last_error", "prt_tile_rays", "prt_scene_create", "prt_scene_destroy",
     "prt_scene_n_leaves", "prt_trace", "prt_scan_runs", "prt_gather_frame", "prt_intersect",
     "prt_generate_source", "prt_fp64_probe", "prt_nearest_hit", "prt_scene_update",
-    "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
+    "prt_render_hit", "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
 )
 
 
@@ -111,6 +111,8 @@ def load():
     lib.prt_generate_source.argtypes = [ctypes.POINTER(PrtSourceDesc), vp, i64, i64, i64, vp]
     lib.prt_nearest_hit.restype = ctypes.c_int
     lib.prt_nearest_hit.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.prt_render_hit.restype = ctypes.c_int
+    lib.prt_render_hit.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.prt_scene_update.restype = ctypes.c_int
     lib.prt_scene_update.argtypes = [vp, vp, vp]
     f64 = ctypes.c_double

@@ -26,6 +26,8 @@ cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int 
 cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
                               long long first, cudaStream_t st);
 cudaError_t prt_launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);
+cudaError_t prt_launch_render_hit(const unsigned char* blob, int blob_bytes, const double* rays, long long n,
+                                  double* t_out, long long* sid_out, double* normals, cudaStream_t st);
 cudaError_t prt_launch_spot_moments(const double* frame, long long rows, long long stride, int select, double value,
                                     long long rays_per_group, int n_groups, const double* center, double* out,
                                     int blocks, cudaStream_t st);
@@ -236,6 +238,18 @@ int prt_nearest_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d
   cudaError_t e = prt_launch_nearest(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
                                      reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "nearest kernel launch");
+  return PRT_OK;
+}
+
+int prt_render_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d_t, int64_t* d_sid, double* d_normals,
+                   void* cuda_stream) {
+  if (!scene) return fail(PRT_ERR_INVALID, "null scene");
+  if (n < 0) return fail(PRT_ERR_INVALID, "negative ray count");
+  if (n == 0) return PRT_OK;
+  if (!d_rays || !d_t || !d_sid) return fail(PRT_ERR_INVALID, "null buffer");
+  cudaError_t e = prt_launch_render_hit(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
+                                        reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "render hit kernel launch");
   return PRT_OK;
 }
 

@@ -345,6 +345,59 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) nearest_kernel(cons
   }
 }
 
+// EdgeRender / ShadedRenderer._st_propagate (tinygfx/g3d/renderers.py:72-94,:188-210): the tracer's loop,
+// except that the distance and surface are read from the *unfiltered* hit array at the argmin of the
+// filtered one -- a pixel whose component hits are all behind the camera reports slot 0, a negative
+// distance.  Needs every hit of every component, so it runs the interpreter without pruning.
+__global__ void __launch_bounds__(kTileRays) render_hit_kernel(const unsigned char* blob, int blob_bytes,
+                                                               const double* rays, long long n, double* t_out,
+                                                               long long* sid_out, double* normals) {
+  extern __shared__ __align__(16) unsigned char s_blob[];
+  {
+    const int words = blob_bytes / 8;
+    const double* src = reinterpret_cast<const double*>(blob);
+    double* dst = reinterpret_cast<double*>(s_blob);
+    for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  const SceneView sc = make_view(s_blob);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
+  const double v0 = rays[4 * n + i], v1 = rays[5 * n + i], v2 = rays[6 * n + i];
+  const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
+  double best_t = PRT_INF;
+  int best_leaf = -1;
+  for (int c = 0; c < sc.h->n_components; ++c) {
+    HitStack S;
+    S.flags = 0;
+    bool tie = false;
+    const bool any = eval_component(sc, sc.comps[c].begin, sc.comps[c].end, p0, p1, p2, v0, v1, v2, inv, false,
+                                    PRT_INF, S, tie);
+    const int len = any ? S.len[0] : 0;
+    if (len == 0) continue;  // culled or empty: every slot is +inf / -1
+    const int b = buf_of(S, 0);
+    int arg = 0;  // ascending list: the first positive entry is the argmin of where(hits > 0, hits, inf)
+    while (arg < len && !(S.t[b][arg] > 0.0)) ++arg;
+    if (arg == len) arg = 0;
+    const double t = S.t[b][arg];
+    if (t < best_t) {
+      best_t = t;
+      best_leaf = S.leaf[b][arg];
+    }
+  }
+  t_out[i] = best_t;
+  sid_out[i] = best_leaf >= 0 ? (long long)sc.leaves[best_leaf].sid : -1;
+  if (normals) {
+    double n0 = CUDART_NAN, n1 = CUDART_NAN, n2 = CUDART_NAN;
+    if (best_leaf >= 0)
+      world_normal(sc.leaves[best_leaf], p0 + v0 * best_t, p1 + v1 * best_t, p2 + v2 * best_t, n0, n1, n2);
+    normals[0 * n + i] = n0;
+    normals[1 * n + i] = n1;
+    normals[2 * n + i] = n2;
+  }
+}
+
 // ---------------------------------------------------------------- K3: seeded synthetic sources
 //
 // Counter-based uniforms u(i,k) = mix64(seed ^ (i*C1 + k*C2)) >> 11 * 2^-53; only + - * / sqrt
@@ -601,6 +654,17 @@ cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const 
     cudaFuncSetAttribute(prt::nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
   prt::nearest_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out, sid_out,
                                                                           normals);
+  return cudaGetLastError();
+}
+
+cudaError_t prt_launch_render_hit(const unsigned char* blob, int blob_bytes, const double* rays, long long n,
+                                  double* t_out, long long* sid_out, double* normals, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + prt::kTileRays - 1) / prt::kTileRays);
+  if (blob_bytes > 48 * 1024)
+    cudaFuncSetAttribute(prt::render_hit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
+  prt::render_hit_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out, sid_out,
+                                                                            normals);
   return cudaGetLastError();
 }
 

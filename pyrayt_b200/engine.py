@@ -196,17 +196,22 @@ class Engine:
         self.scene = scene
         self.n_leaves = scene.n_leaves
 
-    def nearest_hit(self, d_rays, normals: bool = False):
-        """_st_propagate alone: (distance (N,), surface id (N,), world normals (3,N) or None)."""
+    def nearest_hit(self, d_rays, normals: bool = False, renderer: bool = False):
+        """_st_propagate alone: (distance (N,), surface id (N,), world normals (3,N) or None).
+
+        renderer=True: the variant the reference's renderers run (prt_render_hit): a ray whose hits on a
+        component are all behind it picks up that component's first, negative, hit."""
         torch = self._torch
+        entry, what = (self.lib.prt_render_hit, "prt_render_hit") if renderer else \
+            (self.lib.prt_nearest_hit, "prt_nearest_hit")
         r = d_rays.reshape(8, -1).contiguous()
         n = int(r.shape[1])
         t = torch.empty(n, dtype=torch.float64, device=self._dev())
         sid = torch.empty(n, dtype=torch.int64, device=self._dev())
         nrm = torch.empty((3, n), dtype=torch.float64, device=self._dev()) if normals else None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.prt_nearest_hit(self._handle, r.data_ptr(), n, t.data_ptr(), sid.data_ptr(),
-                                                nrm.data_ptr() if normals else None, self._stream()), "prt_nearest_hit")
+            _lib.check(entry(self._handle, r.data_ptr(), n, t.data_ptr(), sid.data_ptr(),
+                             nrm.data_ptr() if normals else None, self._stream()), what)
         return t, sid, nrm
 
     # ------------------------------------------------------------------ component.intersect

@@ -6,7 +6,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+_ALL_NPZ = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN_CASES = [c for c in _ALL_NPZ if not c.startswith("render_")]   # trace frames (make_golden.py)
+RENDER_CASES = [c for c in _ALL_NPZ if c.startswith("render_")]       # renderer hit images (make_render_golden.py)
+
+
+def load_render_case(name):
+    """(FlatScene, camera rays (2,4,N), reference distance (N,), surface (N,), canvas (v,h,4), (h, v))."""
+    from pyrayt_b200.scene import FlatScene
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    scene = FlatScene.from_json(open(os.path.join(GOLDEN_DIR, name + ".scene.json")).read())
+    return scene, z["rays"], z["distance"], z["surface"], z["canvas"], tuple(int(x) for x in z["resolution"])
 
 
 def load_case(name):
