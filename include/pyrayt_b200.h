@@ -202,7 +202,9 @@ int prt_gather_frame(const prt_records* records, int32_t generation_limit, const
 /*
  * component.intersect(rays): d_rays is (2,4,N) like the reference (row k of ray i
  * at d_rays[k*n + i]); writes hits (m,N) ascending with +inf padding and the
- * surface ids (m,N) (-1 where the reference reports -1 or the slot is +inf).
+ * surface ids (m,N) exactly as the reference returns them -- the ids carried by
+ * the +inf slots included (a missed leaf keeps its id, a CSG node whose box was
+ * missed reports -1; tinygfx/g3d/csg.py:126-160).
  * m = 2 x leaves of the component (returned through *slots_out when non-NULL).
  */
 int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int64_t n,

@@ -22,6 +22,7 @@
 #include "../../include/pyrayt_b200.h"
 #include "prt_scene.h"
 #include "prt_device.cuh"
+#include "prt_literal.cuh"
 
 namespace prt {
 
@@ -296,17 +297,15 @@ __global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned cha
   if (i >= n) return;
   const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
   const double v0 = rays[4 * n + i], v1 = rays[5 * n + i], v2 = rays[6 * n + i];
-  HitStack S;
-  S.flags = 0;
-  bool tie = false;
-  const bool any =
-      eval_component(sc, sc.comps[component].begin, sc.comps[component].end, p0, p1, p2, v0, v1, v2,
-                     make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0), false, PRT_INF, S, tie);
-  const int b = buf_of(S, 0);
-  const int len = any ? S.len[0] : 0;
+  // the literal fixed-length lists: +inf slots and the surface ids they carry are part of what
+  // component.intersect returns (prt_literal.cuh)
+  LitList stack[kLitStack];
+  eval_component_literal(sc, sc.comps[component].begin, sc.comps[component].end, p0, p1, p2, v0, v1, v2,
+                         make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0), stack);
+  const LitList& r = stack[0];
   for (int k = 0; k < slots; ++k) {
-    hits[k * n + i] = (k < len) ? S.t[b][k] : PRT_INF;
-    sids[k * n + i] = (k < len) ? (long long)sc.leaves[S.leaf[b][k]].sid : -1;
+    hits[k * n + i] = (k < r.n) ? r.t[k] : PRT_INF;
+    sids[k * n + i] = (k < r.n && r.leaf[k] >= 0) ? (long long)sc.leaves[r.leaf[k]].sid : -1;
   }
 }
 

@@ -1,0 +1,67 @@
+"""Small end-to-end exercise of every kernel, meant to run under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python scripts/sanitize_run.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_run.py
+    compute-sanitizer --tool synccheck python scripts/sanitize_run.py
+
+Golden cases (all record modes, staging overflow + retry), sources, component.intersect, nearest / render hits,
+the ordering kernels and the frame read-outs; every result is compared with the oracle.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import pyrayt_b200  # noqa: E402
+from oracle import oracle, sources_np  # noqa: E402
+from pyrayt_b200 import analytics, workloads  # noqa: E402
+from tests.helpers import GOLDEN_CASES, RENDER_CASES, load_case, load_render_case  # noqa: E402
+
+checked = 0
+for name in GOLDEN_CASES:
+    scene, rays, _, gl = load_case(name)
+    rays = np.ascontiguousarray(rays[:, :700])
+    eng = pyrayt_b200.Engine(scene, 0)
+    d = torch.from_numpy(rays).cuda()
+    want, ctr = oracle.trace(scene, rays, gl)
+    res = eng.trace(d, generation_limit=gl)
+    assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), name
+    res = eng.trace(d, generation_limit=gl, capacity=64, to_host=True)  # overflow, then the exact retry
+    assert np.array_equal(res.frame.numpy(), want, equal_nan=True), name
+    sid = int(scene.leaf_sid[-1])
+    res = eng.trace(d, generation_limit=gl, record="surface", detector_sid=sid)
+    assert np.array_equal(res.frame.cpu().numpy(), want[:, want[5] == sid], equal_nan=True), name
+    assert eng.trace(d, generation_limit=gl, record="none").counters["generations"] == ctr["generations"]
+    full = eng.trace(d, generation_limit=gl)
+    if full.rows:
+        analytics.spot_stats(full, max(1, rays.shape[1] // 3), 3, surface=sid)
+        analytics.focus_table(full, generation=float(want[0].max()))
+    r8 = np.zeros((8, rays.shape[1]))
+    r8[0:3], r8[3], r8[4:7] = rays[0:3], 1, rays[4:7]
+    for renderer in (False, True):
+        t, s, nrm = eng.nearest_hit(torch.from_numpy(r8).cuda(), normals=True, renderer=renderer)
+        ot, osid, onrm = (oracle.render_hit if renderer else oracle.nearest)(scene, r8)
+        assert np.array_equal(t.cpu().numpy(), ot) and np.array_equal(s.cpu().numpy(), osid), name
+    for c in range(scene.n_components):
+        hits, sids = eng.intersect(c, torch.from_numpy(r8.reshape(2, 4, -1)).cuda())
+        oh, os_ = oracle.intersect(scene, c, r8.reshape(2, 4, -1))
+        hits, sids = hits.cpu().numpy(), sids.cpu().numpy()
+        assert np.array_equal(hits, oh, equal_nan=True) and np.array_equal(sids, os_), name
+    eng.close()
+    checked += 1
+for name in RENDER_CASES:
+    scene, rays, dist, surf, _, _ = load_render_case(name)
+    eng = pyrayt_b200.Engine(scene, 0)
+    t, s, _ = eng.nearest_hit(torch.from_numpy(np.ascontiguousarray(rays[..., :1500])).cuda(), renderer=True)
+    assert np.array_equal(s.cpu().numpy(), surf[:1500]), name
+    checked += 1
+for wl in workloads.WORKLOADS.values():
+    got = wl.source.generate(1000, device=0, first_index=77).cpu().numpy()
+    assert np.array_equal(got, sources_np.from_source(wl.source, 1000, first_index=77)), wl.name
+    checked += 1
+torch.cuda.synchronize()
+print(f"sanitize_run: {checked} groups checked against the oracle")

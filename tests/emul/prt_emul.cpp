@@ -13,6 +13,7 @@ using std::isinf;
 using std::isnan;
 
 #include "../../pyrayt_b200/csrc/prt_device.cuh"
+#include "../../pyrayt_b200/csrc/prt_literal.cuh"
 #include "../../pyrayt_b200/csrc/prt_encode.h"
 
 extern "C" {
@@ -86,20 +87,28 @@ int prt_emul_intersect(const prt_scene_desc* d, int comp, const double* rays, lo
   const prt::SceneView sc = prt::make_view(blob.data());
   const int m = slots[comp];
   for (long long i = 0; i < n; ++i) {
+    std::vector<prt::LitList> stack(prt::kLitStack);
+    const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
+    const double v0 = rays[4 * n + i], v1 = rays[5 * n + i], v2 = rays[6 * n + i];
+    prt::eval_component_literal(sc, sc.comps[comp].begin, sc.comps[comp].end, p0, p1, p2, v0, v1, v2,
+                                prt::make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0), stack.data());
+    const prt::LitList& r = stack[0];
+    // the streaming evaluation the trace kernel uses must agree on every finite slot
     prt::HitStack S;
     S.flags = 0;
     bool tie = false;
-    const bool any = prt::eval_component(
-        sc, sc.comps[comp].begin, sc.comps[comp].end, rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i],
-        rays[5 * n + i], rays[6 * n + i],
-        prt::make_ray_inv(rays[0 * n + i], rays[1 * n + i], rays[2 * n + i], rays[4 * n + i], rays[5 * n + i],
-                          rays[6 * n + i], (sc.h->flags & 1) != 0),
-        false, INFINITY, S, tie);
+    const bool any = prt::eval_component(sc, sc.comps[comp].begin, sc.comps[comp].end, p0, p1, p2, v0, v1, v2,
+                                         prt::make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0), false,
+                                         INFINITY, S, tie);
     const int b = prt::buf_of(S, 0);
     const int len = any ? S.len[0] : 0;
+    if (r.n != m) return -2;
     for (int k = 0; k < m; ++k) {
-      hits[k * n + i] = (k < len) ? S.t[b][k] : INFINITY;
-      sids[k * n + i] = (k < len) ? (long long)sc.leaves[S.leaf[b][k]].sid : -1;
+      const bool fin = r.t[k] < INFINITY;
+      if (fin != (k < len)) return -3;
+      if (fin && (S.t[b][k] != r.t[k] || (int)S.leaf[b][k] != (int)r.leaf[k])) return -4;
+      hits[k * n + i] = r.t[k];
+      sids[k * n + i] = r.leaf[k] >= 0 ? (long long)sc.leaves[r.leaf[k]].sid : -1;
     }
   }
   return 0;
