@@ -158,6 +158,106 @@ class Engine:
             launches += 1 if rows else 0
             return TraceResult(frame, rows, counters, gen_counts, launches, self.n_leaves)
 
+    # ------------------------------------------------------------------ many small traces (N4)
+    SMALL_MAX_RAYS = 4096
+    SMALL_MAX_ROWS = 1 << 16
+
+    def small_fits(self, n: int, generation_limit: int) -> bool:
+        return 0 < n <= self.SMALL_MAX_RAYS and n * int(generation_limit) <= self.SMALL_MAX_ROWS
+
+    def small_ray_buffer(self, n: int):
+        """Persistent (13, n) device RaySet for trace_small: fill it (sources, or one H2D copy) and call
+        trace_small(n, ...).  Its address is part of the captured launch sequence."""
+        torch = self._torch
+        t = self._ws.get(("small_rays", n))
+        if t is None:
+            t = torch.zeros((_lib.RAY_ROWS, n), dtype=torch.float64, device=self._dev())
+            self._ws[("small_rays", n)] = t
+        return t
+
+    def trace_small(self, n: int, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
+                    detector_sid: int = -1, use_graph: bool = True) -> TraceResult:
+        """Latency path for the optimiser loops of examples/lens_design.ipynb (cells 28-33: thousands of
+        traces of <= 21 rays through a system whose radii change in between).
+
+        The staging buffer is sized for the worst case (n x generation_limit rows), so nothing depends
+        on a count read back mid-way: clear -> trace -> scan -> gather -> two D2H copies are enqueued
+        back to back, captured once into a CUDA graph per (n, generation_limit, record mode) and
+        replayed with one launch and one synchronisation per trace.  The scene is read from its device
+        blob at run time, so prt_scene_update between replays is seen by the next one.
+        """
+        torch = self._torch
+        G = int(generation_limit)
+        if not self.small_fits(n, G):
+            raise _lib.PrtError("trace_small is for small ray sets; use trace()")
+        mode = _RECORD_MODES[record]
+        if mode == _lib.RECORD_NONE:
+            raise _lib.PrtError("trace_small records rows; use trace(record='none') for counters only")
+        key = ("small", n, G, mode, int(detector_sid), float(ray_offset))
+        st = self._ws.get(key)
+        with torch.cuda.device(self.device):
+            if st is None:
+                st = self._small_state(n, G, mode, detector_sid, ray_offset)
+                self._ws[key] = st
+            if use_graph and st["graph"] is None and st["uses"] >= 1:
+                # capture on the second use: the first one ran eagerly (module load, attribute calls)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._small_enqueue(st)
+                st["graph"] = g
+            if use_graph and st["graph"] is not None:
+                st["graph"].replay()
+            else:
+                self._small_enqueue(st)
+            st["uses"] += 1
+            torch.cuda.current_stream(self.device).synchronize()
+        meta = st["h_meta"]
+        counters = dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in meta[: len(_lib.COUNTER_FIELDS)])))
+        goff = meta[_lib.COUNTER_WORDS: _lib.COUNTER_WORDS + G + 1].numpy()
+        rows = int(goff[G])
+        frame = st["h_frame"][:, :rows].clone()  # the pinned buffer is overwritten by the next replay
+        return TraceResult(frame, rows, counters, np.diff(goff).astype(np.int64), st["launches"], self.n_leaves)
+
+    def _small_state(self, n, G, mode, detector_sid, ray_offset):
+        torch = self._torch
+        dev = self._dev()
+        cap = n * G
+        n_tiles = max(1, (n + self.tile - 1) // self.tile)
+        # [counters | generation offsets] and the run counts are cleared / read back together
+        meta = torch.zeros(_lib.COUNTER_WORDS + G + 1, dtype=torch.int64, device=dev)
+        run_count = torch.zeros(G * n_tiles, dtype=torch.int32, device=dev)
+        st = {
+            "n": n, "G": G, "cap": cap, "meta": meta, "run_count": run_count,
+            "run_start": torch.zeros(G * n_tiles, dtype=torch.int64, device=dev),
+            "run_base": torch.zeros(G * n_tiles, dtype=torch.int64, device=dev),
+            "stage": torch.empty(_lib.FRAME_COLS * cap, dtype=torch.float64, device=dev),
+            "frame": torch.zeros((_lib.FRAME_COLS, cap), dtype=torch.float64, device=dev),
+            "h_meta": torch.zeros(_lib.COUNTER_WORDS + G + 1, dtype=torch.int64).pin_memory(),
+            "h_frame": torch.zeros((_lib.FRAME_COLS, cap), dtype=torch.float64).pin_memory(),
+            "rays": self.small_ray_buffer(n),
+            "params": _lib.PrtParams(G, mode, 0, 0, float(ray_offset), int(detector_sid)),
+            "graph": None, "uses": 0, "launches": 4,
+        }
+        st["rec"] = _lib.PrtRecords(st["stage"].data_ptr(), cap, st["run_start"].data_ptr(), run_count.data_ptr(),
+                                    st["run_base"].data_ptr(), n_tiles)
+        return st
+
+    def _small_enqueue(self, st):
+        n, G = st["n"], st["G"]
+        meta, rays = st["meta"], st["rays"]
+        stream = self._stream()
+        meta.zero_()
+        st["run_count"].zero_()
+        _lib.check(self.lib.prt_trace(self._handle, ctypes.byref(st["params"]), rays.data_ptr(), n, int(rays.stride(0)),
+                                      ctypes.byref(st["rec"]), meta.data_ptr(), stream), "prt_trace")
+        gen_off = meta[_lib.COUNTER_WORDS:]
+        _lib.check(self.lib.prt_scan_runs(ctypes.byref(st["rec"]), G, gen_off.data_ptr(), stream), "prt_scan_runs")
+        _lib.check(self.lib.prt_gather_frame(ctypes.byref(st["rec"]), G, gen_off.data_ptr(), st["frame"].data_ptr(),
+                                             st["cap"], 0, stream), "prt_gather_frame")
+        st["h_meta"].copy_(meta, non_blocking=True)
+        st["h_frame"].copy_(st["frame"], non_blocking=True)
+
     def _gather(self, rec, G, gen_off, rows, to_host, host_frame, zero_copy):
         torch = self._torch
         if rows == 0:
@@ -191,6 +291,12 @@ class Engine:
     def update_scene(self, scene: FlatScene) -> None:
         """Re-encode a (moved / re-parameterised) scene into this engine without re-creating it."""
         desc = scene.as_desc()
+        same_structure = (np.array_equal(scene.node_kind, self.scene.node_kind)
+                          and np.array_equal(scene.comp_node_begin, self.scene.comp_node_begin)
+                          and np.array_equal(scene.leaf_type, self.scene.leaf_type))
+        if not same_structure:  # captured launch sequences hold the blob size and the kernel variant
+            for st in [v for k, v in self._ws.items() if isinstance(k, tuple) and k[0] == "small"]:
+                st["graph"], st["uses"] = None, 0
         with self._torch.cuda.device(self.device):
             _lib.check(self.lib.prt_scene_update(self._handle, ctypes.byref(desc), self._stream()), "prt_scene_update")
         self.scene = scene

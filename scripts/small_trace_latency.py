@@ -33,3 +33,11 @@ t0 = time.perf_counter()
 for k in range(200):
     res = eng.trace(rays, generation_limit=10, to_host=True)
 print(f"Engine.trace() 21 rays to host: {(time.perf_counter() - t0) / 200 * 1e3:.3f} ms per call")
+eng.small_ray_buffer(21).copy_(rays)
+for label, graph in (("eager launches", False), ("CUDA graph replay", True)):
+    for k in range(3):
+        eng.trace_small(21, generation_limit=10, use_graph=graph)
+    t0 = time.perf_counter()
+    for k in range(500):
+        res = eng.trace_small(21, generation_limit=10, use_graph=graph)
+    print(f"Engine.trace_small() 21 rays to host, {label}: {(time.perf_counter() - t0) / 500 * 1e3:.3f} ms per call")

@@ -274,3 +274,53 @@ def test_camera_nearest_image_matches_oracle(torch_mod):
     assert {-1, ball.get_id(), lens._l_child.get_id()} <= set(np.unique(sid).tolist())
     canvas = pyrayt_b200.render.edge_canvas(img["surface"])
     assert canvas.shape == (72, 96, 4) and 0 < canvas[..., 3].mean() < 0.5
+
+
+def test_trace_small_replays_match_trace(torch_mod):
+    """N4: the captured launch sequence for small ray sets gives the frame of the ordinary path, trace
+    after trace, also when the scene is re-encoded in place between replays."""
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+
+    for name in ("config1_collimator", "thick_lens_zoo", "facing_mirrors", "config5_cavity"):
+        scene, rays, _, gl = load_case(name)
+        gl = min(gl, 24)
+        rays = np.ascontiguousarray(rays[:, :300])
+        n = rays.shape[1]
+        eng = pyrayt_b200.Engine(scene, device=0)
+        want, octr = oracle.trace(scene, rays, gl)
+        eng.small_ray_buffer(n).copy_(torch_mod.from_numpy(rays))
+        for rep in range(4):  # eager, capture + replay, replay, replay
+            res = eng.trace_small(n, generation_limit=gl)
+            assert res.rows == want.shape[1] and np.array_equal(res.frame.numpy(), want, equal_nan=True), (name, rep)
+            assert res.counters["segments"] == octr["segments"] and res.counters["rows_dropped"] == 0
+            assert np.array_equal(res.gen_counts, np.bincount(want[0].astype(int), minlength=gl)[:gl])
+        sid = int(scene.leaf_sid[-1])
+        for rep in range(3):
+            res = eng.trace_small(n, generation_limit=gl, record="surface", detector_sid=sid)
+            assert np.array_equal(res.frame.numpy(), want[:, want[5] == sid], equal_nan=True)
+        eager = eng.trace_small(n, generation_limit=gl, use_graph=False)
+        assert np.array_equal(eager.frame.numpy(), want, equal_nan=True)
+    # in-place scene updates between replays: same structure (graph kept), then another structure (re-captured)
+    s1, rays = su.random_scene_and_rays(11, n_rays=200)
+    eng = pyrayt_b200.Engine(s1, device=0)
+    eng.small_ray_buffer(200).copy_(torch_mod.from_numpy(rays))
+    for rep in range(3):
+        eng.trace_small(200, generation_limit=12)
+    moved = pyrayt_b200.FlatScene.from_json(s1.to_json())
+    moved.leaf_obj = moved.leaf_obj.copy()
+    moved.leaf_obj.reshape(-1, 4, 4)[:, 0, 3] += 0.05  # shift every surface in object space
+    eng.update_scene(moved)
+    got = eng.trace_small(200, generation_limit=12)
+    want, _ = oracle.trace(moved, rays, 12)
+    assert np.array_equal(got.frame.numpy(), want, equal_nan=True)
+    s2, rays2 = su.random_scene_and_rays(12, n_rays=200)
+    eng.update_scene(s2)
+    eng.small_ray_buffer(200).copy_(torch_mod.from_numpy(rays2))
+    for rep in range(3):
+        got = eng.trace_small(200, generation_limit=12)
+        want, _ = oracle.trace(s2, rays2, 12)
+        assert np.array_equal(got.frame.numpy(), want, equal_nan=True)
+    with pytest.raises(pyrayt_b200.PrtError):
+        eng.trace_small(5000, generation_limit=10)
