@@ -181,6 +181,38 @@ int prt_trace(prt_scene* scene, const prt_params* params, const double* d_rays, 
               void* cuda_stream);
 
 /*
+ * The same trace for large ray sets, one launch per generation ("wavefront"): launch g finishes
+ * generation g-1 (interaction, row, new state) and starts generation g (nearest hit, per-tile count of
+ * the rows it will produce); a scan between two launches turns the counts into positions, so every
+ * row is written straight to its final (generation, id) place in d_frame (column-major, column c row
+ * r at d_frame[c*frame_stride + r], at most `capacity` rows; further rows are counted in
+ * d_counters->rows_dropped, and d_counters->rows_reserved receives the exact row count).  No staging
+ * buffer, no ordering pass; the frame is bit-identical to prt_trace + prt_scan_runs + prt_gather_frame.
+ * All 2 x generation_limit + 1 launches are enqueued by this call; launches for generations no ray
+ * reaches return immediately on the device.  d_gen_offsets[g] (g = 0 .. generation_limit) receives
+ * the first frame row of generation g, d_gen_offsets[generation_limit] the row count.  record_mode
+ * PRT_RECORD_NONE is not supported here (use prt_trace).
+ * step_events (optional, may be NULL): 2 x (generation_limit + 1) cudaEvent_t handles recorded
+ * before and after each launch of the step kernel, for timing that kernel alone.
+ */
+typedef struct prt_wave_workspace {
+  double* d_state;       /* [7 * n_rays] position, direction, refractive index of every ray        */
+  int32_t* d_flag;       /* [n_rays]                                                               */
+  double* d_hit_t;       /* [n_rays]                                                               */
+  int32_t* d_hit_leaf;   /* [n_rays]                                                               */
+  int32_t* d_tile_count; /* [2 * n_tiles] rows each tile writes, by generation parity              */
+  int64_t* d_tile_base;  /* [2 * n_tiles]                                                          */
+  int64_t* d_alive;      /* [generation_limit + 1] live rays entering each generation              */
+  int64_t n_tiles;       /* >= ceil(n_rays / prt_wave_tile())                                      */
+} prt_wave_workspace;
+
+int prt_wave_tile(void);
+int prt_trace_wavefront(prt_scene* scene, const prt_params* params, const double* d_rays, int64_t n_rays,
+                        int64_t ray_stride, const prt_wave_workspace* ws, double* d_frame,
+                        int64_t frame_stride, int64_t capacity, int64_t* d_gen_offsets,
+                        prt_counters* d_counters, void** step_events, void* cuda_stream);
+
+/*
  * Turn the run table into final frame positions: d_gen_offsets[g] (g = 0 ..
  * generation_limit) receives the first frame row of generation g and
  * d_gen_offsets[generation_limit] the total row count.  The caller may rewrite

@@ -35,7 +35,7 @@ EXPORTS = (
     "prt_abi_version", "prt_last_error", "prt_tile_rays", "prt_scene_create", "prt_scene_destroy",
     "prt_scene_n_leaves", "prt_trace", "prt_scan_runs", "prt_gather_frame", "prt_intersect",
     "prt_generate_source", "prt_fp64_probe", "prt_nearest_hit", "prt_scene_update",
-    "prt_render_hit", "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
+    "prt_render_hit", "prt_wave_tile", "prt_trace_wavefront", "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
 )
 
 
@@ -61,6 +61,19 @@ class PrtRecords(ctypes.Structure):
         ("d_run_start", ctypes.c_void_p),
         ("d_run_count", ctypes.c_void_p),
         ("d_run_base", ctypes.c_void_p),
+        ("n_tiles", ctypes.c_int64),
+    ]
+
+
+class PrtWaveWorkspace(ctypes.Structure):
+    _fields_ = [
+        ("d_state", ctypes.c_void_p),
+        ("d_flag", ctypes.c_void_p),
+        ("d_hit_t", ctypes.c_void_p),
+        ("d_hit_leaf", ctypes.c_void_p),
+        ("d_tile_count", ctypes.c_void_p),
+        ("d_tile_base", ctypes.c_void_p),
+        ("d_alive", ctypes.c_void_p),
         ("n_tiles", ctypes.c_int64),
     ]
 
@@ -101,6 +114,10 @@ def load():
     lib.prt_scene_n_leaves.argtypes = [vp]
     lib.prt_trace.restype = ctypes.c_int
     lib.prt_trace.argtypes = [vp, ctypes.POINTER(PrtParams), vp, i64, i64, ctypes.POINTER(PrtRecords), vp, vp]
+    lib.prt_wave_tile.restype = ctypes.c_int
+    lib.prt_trace_wavefront.restype = ctypes.c_int
+    lib.prt_trace_wavefront.argtypes = [vp, ctypes.POINTER(PrtParams), vp, i64, i64, ctypes.POINTER(PrtWaveWorkspace),
+                                        vp, i64, i64, vp, vp, vp, vp]
     lib.prt_scan_runs.restype = ctypes.c_int
     lib.prt_scan_runs.argtypes = [ctypes.POINTER(PrtRecords), i32, vp, vp]
     lib.prt_gather_frame.restype = ctypes.c_int

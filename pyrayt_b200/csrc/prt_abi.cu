@@ -41,6 +41,32 @@ cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const 
                                long long* sid_out, double* normals, cudaStream_t st);
 }
 
+// mirrors prt::WaveArgs (prt_wavefront.cu)
+struct WaveArgsAbi {
+  const unsigned char* blob;
+  int blob_bytes;
+  int generation_limit;
+  int record_mode;
+  int g;
+  double ray_offset;
+  double detector_sid;
+  const double* rays;
+  long long n_rays, stride;
+  double* st;
+  int* flag;
+  double* hit_t;
+  int* hit_leaf;
+  int* blk_count;
+  long long* blk_base;
+  long long* alive;
+  long long* gen_off;
+  long long n_tiles;
+  double* frame;
+  long long frame_stride, capacity;
+  prt_counters* ctr;
+};
+extern "C" cudaError_t prt_launch_wavefront(WaveArgsAbi* a, int generic, cudaEvent_t* events, cudaStream_t st);
+
 struct prt_scene {
   int device = 0;
   unsigned char* d_blob = nullptr;
@@ -186,6 +212,54 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
   a.ctr = d_counters;
   cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, scene->generic, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "trace kernel launch");
+  return PRT_OK;
+}
+
+int prt_trace_wavefront(prt_scene* scene, const prt_params* p, const double* d_rays, int64_t n_rays,
+                        int64_t ray_stride, const prt_wave_workspace* ws, double* d_frame, int64_t frame_stride,
+                        int64_t capacity, int64_t* d_gen_offsets, prt_counters* d_counters, void** nearest_events,
+                        void* cuda_stream) {
+  if (!scene || !p || !d_counters || !ws || !d_gen_offsets) return fail(PRT_ERR_INVALID, "null argument");
+  if (n_rays < 0 || (n_rays > 0 && !d_rays)) return fail(PRT_ERR_INVALID, "bad ray buffer");
+  if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
+  if (p->generation_limit < 1) return fail(PRT_ERR_INVALID, "generation_limit must be >= 1");
+  if (p->generation_limit > 65535) return fail(PRT_ERR_LIMIT, "generation_limit must be <= 65535");
+  if (p->record_mode != PRT_RECORD_ALL && p->record_mode != PRT_RECORD_SURFACE)
+    return fail(PRT_ERR_INVALID, "the wavefront trace records rows: record_mode must be ALL or SURFACE");
+  const int64_t tiles = (n_rays + prt_wave_tile() - 1) / prt_wave_tile();
+  if (tiles > 0x7fffffffLL) return fail(PRT_ERR_LIMIT, "too many rays for one launch");
+  if (ws->n_tiles < tiles) return fail(PRT_ERR_INVALID, "workspace.n_tiles too small");
+  if (n_rays > 0 && (!ws->d_state || !ws->d_flag || !ws->d_hit_t || !ws->d_hit_leaf || !ws->d_tile_count ||
+                     !ws->d_tile_base))
+    return fail(PRT_ERR_INVALID, "workspace buffer missing");
+  if (!ws->d_alive) return fail(PRT_ERR_INVALID, "workspace buffer missing");
+  if (capacity < 0 || (capacity > 0 && !d_frame) || frame_stride < capacity) return fail(PRT_ERR_INVALID, "bad frame");
+  WaveArgsAbi a;
+  std::memset(&a, 0, sizeof a);
+  a.blob = scene->d_blob;
+  a.blob_bytes = scene->blob_bytes;
+  a.generation_limit = p->generation_limit;
+  a.record_mode = p->record_mode;
+  a.ray_offset = p->ray_offset;
+  a.detector_sid = (double)p->detector_sid;
+  a.rays = d_rays;
+  a.n_rays = n_rays;
+  a.stride = ray_stride;
+  a.st = ws->d_state;
+  a.flag = ws->d_flag;
+  a.hit_t = ws->d_hit_t;
+  a.hit_leaf = ws->d_hit_leaf;
+  a.blk_count = ws->d_tile_count;
+  a.blk_base = reinterpret_cast<long long*>(ws->d_tile_base);
+  a.alive = reinterpret_cast<long long*>(ws->d_alive);
+  a.gen_off = reinterpret_cast<long long*>(d_gen_offsets);
+  a.frame = d_frame;
+  a.frame_stride = frame_stride;
+  a.capacity = capacity;
+  a.ctr = d_counters;
+  cudaError_t e = prt_launch_wavefront(&a, scene->generic, reinterpret_cast<cudaEvent_t*>(nearest_events),
+                                       (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "wavefront launch");
   return PRT_OK;
 }
 

@@ -14,7 +14,7 @@
 
 #if defined(__CUDACC__)
 #define PRT_HD __host__ __device__ __forceinline__
-#define PRT_HD_CALL __host__ __device__ __noinline__  // one copy in the kernel: keeps the hot loop inside the I-cache
+#define PRT_HD_CALL static __host__ __device__ __noinline__  // one copy in the kernel: keeps the hot loop inside the I-cache
 #else
 #define PRT_HD inline
 #define PRT_HD_CALL inline
@@ -836,8 +836,6 @@ struct StepCounters {
 constexpr unsigned kCtrTie = 1u << 16, kCtrUntr = 1u << 17, kCtrNan = 1u << 18, kCtrLim = 1u << 19,
                    kCtrAbs = 1u << 20;
 
-// _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
-// returns true when the ray goes on to generation g+1.
 // A ray that leaves a convex solid through one of its faces (its new direction has a clearly positive
 // component along the outward normal there) cannot hit that solid again until it changes direction:
 // the whole solid lies behind the tangent plane.  Returns that component for the next generation's
@@ -847,23 +845,22 @@ PRT_HD int leaves_for_good(const SceneView& sc, const Leaf& L, double out_dot) {
   return ((L.comp >= 0) && (out_dot > 1e-3) && (sc.comps[L.comp].flags & 2)) ? L.comp : -1;
 }
 
-template <bool GENERIC>
-PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int generation_limit, HitStack* S,
-                       StepOut& o, StepCounters& c) {
-  o.row = false;
+// first half of a generation: is the ray still travelling?  Returns its speed |v| (0: it is not)
+PRT_HD double step_speed(const RayState& r, StepCounters& c) {
   const double vn = sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
-  if (isz(vn)) return false;  // absorbed / zero direction (_pyrayt.py:415)
+  if (isz(vn)) return 0.0;  // absorbed / zero direction (_pyrayt.py:415)
   if (isnan(r.v0) | isnan(r.v1) | isnan(r.v2)) {
     c.w1 |= kCtrNan;  // every hit compares false in the reference -> miss
-    return false;
+    return 0.0;
   }
   c.w0 += 1u;
-  double best_t;
-  int best_leaf;
-  bool tie = false;
-  nearest_hit<GENERIC>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, r.skip, S, best_t, best_leaf, tie);
-  if (tie) c.w1 |= kCtrTie;
-  if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
+  return vn;
+}
+
+// second half: _st_interact for a ray whose nearest hit is (best_t, best_leaf >= 0); `vn` = step_speed
+PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int generation_limit, double vn,
+                          double best_t, int best_leaf, StepOut& o, StepCounters& c) {
+  o.row = false;
   const Leaf& L = sc.leaves[best_leaf];
   o.e0 = r.p0 + r.v0 * best_t;  // :404-407
   o.e1 = r.p1 + r.v1 * best_t;
@@ -943,6 +940,36 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   }
   return goes_on;
 }
+
+
+// _st_propagate + _st_interact for one ray (pyrayt/_pyrayt.py:370-452).  Fills `o`;
+// returns true when the ray goes on to generation g+1.
+template <bool GENERIC>
+PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int generation_limit, HitStack* S,
+                       StepOut& o, StepCounters& c) {
+  o.row = false;
+  const double vn = step_speed(r, c);
+  if (vn == 0.0) return false;
+  double best_t;
+  int best_leaf;
+  bool tie = false;
+  nearest_hit<GENERIC>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, r.skip, S, best_t, best_leaf, tie);
+  if (tie) c.w1 |= kCtrTie;
+  if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
+  return step_interact(sc, r, g, generation_limit, vn, best_t, best_leaf, o, c);
+}
+
+// storage for the generic interpreter's hit lists: only the GENERIC kernel variants carry it
+template <bool GENERIC>
+struct StackFor {
+  typedef HitStack type;
+  PRT_HD static HitStack* ptr(HitStack& s) { return &s; }
+};
+template <>
+struct StackFor<false> {
+  typedef char type;
+  PRT_HD static HitStack* ptr(char&) { return nullptr; }
+};
 
 // generation g -> g+1 (pyrayt/_pyrayt.py:436-449)
 PRT_HD void advance_ray(RayState& r, const StepOut& o, int g, double ray_offset) {

@@ -33,17 +33,6 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
   return v;
 }
 
-template <bool GENERIC>
-struct StackFor {
-  typedef HitStack type;
-  __device__ static HitStack* ptr(HitStack& s) { return &s; }
-};
-template <>
-struct StackFor<false> {
-  typedef char type;
-  __device__ static HitStack* ptr(char&) { return nullptr; }
-};
-
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 2
 #endif

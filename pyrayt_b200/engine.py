@@ -92,8 +92,13 @@ class Engine:
     # ------------------------------------------------------------------ trace
     def trace(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
               detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
-              host_frame=None, zero_copy: bool = False, k1_events=None) -> TraceResult:
+              host_frame=None, zero_copy: bool = False, k1_events=None, method: str = "auto") -> TraceResult:
         """Trace a device RaySet.
+
+        method: "single" = one kernel for all generations + ordering pass (staging buffer and frame: 240 B
+        of device memory per row); "wavefront" = one launch per generation writing rows in place
+        (trace_wavefront: 120 B per row, same frame, a few per cent slower); "auto" = "single" unless
+        staging + frame would not fit the device.
 
         d_rays: torch float64 CUDA tensor (13, N) in the reference RaySet layout.
         to_host: return the frame in pinned host memory (one D2H copy, or with
@@ -108,6 +113,15 @@ class Engine:
         stride = int(d_rays.stride(0)) if n > 0 else 0
         G = int(generation_limit)
         mode = _RECORD_MODES[record]
+        if method not in ("auto", "single", "wavefront"):
+            raise ValueError("method must be 'auto', 'single' or 'wavefront'")
+        if mode != _lib.RECORD_NONE and not zero_copy and k1_events is None and method != "single":
+            rows_guess = capacity if capacity is not None else min(n * G, n * self.rows_per_ray_hint * 1.05)
+            total = torch.cuda.get_device_properties(self.device).total_memory
+            if method == "wavefront" or 2 * 8 * _lib.FRAME_COLS * rows_guess > 0.8 * total:
+                return self.trace_wavefront(d_rays, generation_limit=G, ray_offset=ray_offset, record=record,
+                                            detector_sid=detector_sid, capacity=capacity, to_host=to_host,
+                                            host_frame=host_frame)
         n_tiles = max(1, (n + self.tile - 1) // self.tile)
         launches = 0
         with torch.cuda.device(self.device):
@@ -157,6 +171,83 @@ class Engine:
             frame = self._gather(rec, G, gen_off, rows, to_host, host_frame, zero_copy)
             launches += 1 if rows else 0
             return TraceResult(frame, rows, counters, gen_counts, launches, self.n_leaves)
+
+    # ------------------------------------------------------------------ large ray sets: one generation per launch
+    WAVEFRONT_MIN_RAYS = 1 << 18
+
+    def trace_wavefront(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
+                        detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
+                        host_frame=None, nearest_events=None) -> TraceResult:
+        """Same result as trace(), computed generation by generation (prt_trace_wavefront): every row is
+        written straight to its final frame position, so there is no staging buffer and no ordering
+        pass.  The device frame is a (15, rows) view of a (15, capacity) buffer.
+
+        nearest_events: optional list that receives (start, end) torch CUDA events around each launch
+        of the step kernel (generation_limit + 1 of them; bench.py times the dominant kernel with them).
+        """
+        torch = self._torch
+        assert d_rays.is_cuda and d_rays.dtype == torch.float64 and d_rays.dim() == 2
+        assert d_rays.shape[0] == _lib.RAY_ROWS and d_rays.stride(1) == 1
+        n = int(d_rays.shape[1])
+        stride = int(d_rays.stride(0)) if n > 0 else 0
+        G = int(generation_limit)
+        mode = _RECORD_MODES[record]
+        if mode == _lib.RECORD_NONE:
+            raise _lib.PrtError("trace_wavefront records rows; use trace(record='none') for counters only")
+        wtile = self.lib.prt_wave_tile()
+        n_tiles = max(1, (n + wtile - 1) // wtile)
+        with torch.cuda.device(self.device):
+            ctr = self._buf("ctr", _lib.COUNTER_WORDS, torch.int64)
+            gen_off = self._buf("gen_off", G + 1, torch.int64)
+            ws = _lib.PrtWaveWorkspace(
+                self._buf("w_state", 7 * max(n, 1), torch.float64).data_ptr(),
+                self._buf("w_flag", max(n, 1), torch.int32).data_ptr(),
+                self._buf("w_hit_t", max(n, 1), torch.float64).data_ptr(),
+                self._buf("w_hit_leaf", max(n, 1), torch.int32).data_ptr(),
+                self._buf("w_tile_count", 2 * n_tiles, torch.int32).data_ptr(),
+                self._buf("w_tile_base", 2 * n_tiles, torch.int64).data_ptr(),
+                self._buf("w_alive", G + 1, torch.int64).data_ptr(), n_tiles)
+            params = _lib.PrtParams(G, mode, 0, 0, float(ray_offset), int(detector_sid))
+            events = None
+            if nearest_events is not None:
+                pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                         for _ in range(G + 1)]
+                for e0, e1 in pairs:  # a torch event gets its CUDA handle at its first record()
+                    e0.record()
+                    e1.record()
+                events = (ctypes.c_void_p * (2 * G + 2))(*[ev.cuda_event for pair in pairs for ev in pair])
+                nearest_events[:] = pairs
+            cap = int(capacity) if capacity is not None else int(min(n * G, max(n * self.rows_per_ray_hint * 1.02, 4096)))
+            cap = max(cap, 1)
+            frame = None
+            while True:
+                frame = None  # (a retry frees the short buffer first)
+                frame = torch.empty((_lib.FRAME_COLS, cap), dtype=torch.float64, device=self._dev())
+                ctr.zero_()
+                _lib.check(self.lib.prt_trace_wavefront(self._handle, ctypes.byref(params), d_rays.data_ptr(), n, stride,
+                                                        ctypes.byref(ws), frame.data_ptr(), cap, cap,
+                                                        gen_off.data_ptr(), ctr.data_ptr(), events, self._stream()),
+                           "prt_trace_wavefront")
+                host = torch.cat([ctr, gen_off[: G + 1]]).cpu()  # one small D2H + sync
+                counters = dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in host[: len(_lib.COUNTER_FIELDS)])))
+                goff = host[_lib.COUNTER_WORDS:].numpy()
+                if counters["rows_dropped"] == 0:
+                    break
+                cap = int(counters["rows_reserved"])  # the kernels kept counting: retry once with the exact size
+            rows = int(goff[G])
+            if n > 0:
+                self.rows_per_ray_hint = max(self.rows_per_ray_hint, rows / n)
+            gen_counts = np.diff(goff).astype(np.int64)
+            launches = 2 * G + 1
+            out = frame[:, :rows]
+            if to_host:
+                pinned = host_frame if host_frame is not None else torch.empty(
+                    (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
+                for c in range(_lib.FRAME_COLS):  # column by column: each one is contiguous on both sides
+                    pinned[c, :rows].copy_(out[c], non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                out = pinned[:, :rows]
+            return TraceResult(out, rows, counters, gen_counts, launches, self.n_leaves)
 
     # ------------------------------------------------------------------ many small traces (N4)
     SMALL_MAX_RAYS = 4096

@@ -27,7 +27,7 @@ def main():
     base = inst[0][0]
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=td, capture_output=True)
-        cub = [f for f in os.listdir(td) if f.startswith("prt_kernels.") and f.endswith(".cubin")][0]
+        cub = [f for f in os.listdir(td) if f.startswith(os.environ.get("HOT_CUBIN", "prt_kernels") + ".") and f.endswith(".cubin")][0]
         dis = subprocess.run(["nvdisasm", "-g", os.path.join(td, cub)], capture_output=True, text=True).stdout
     lines = dis.splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith(".text." + func + ":"))

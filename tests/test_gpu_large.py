@@ -324,3 +324,51 @@ def test_trace_small_replays_match_trace(torch_mod):
         assert np.array_equal(got.frame.numpy(), want, equal_nan=True)
     with pytest.raises(pyrayt_b200.PrtError):
         eng.trace_small(5000, generation_limit=10)
+
+
+def test_wavefront_trace_is_bit_identical_to_single_kernel_trace(torch_mod):
+    """prt_trace_wavefront writes rows straight to their (generation, id) positions: same frame, same
+    counters as prt_trace + scan + gather and as the oracle; overflow retry and record modes included."""
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+    from tests.helpers import GOLDEN_CASES
+
+    for name in GOLDEN_CASES:
+        scene, rays, _, gl = load_case(name)
+        eng = pyrayt_b200.Engine(scene, device=0)
+        d = torch_mod.from_numpy(np.ascontiguousarray(rays)).cuda()
+        want, octr = oracle.trace(scene, rays, gl)
+        ref = eng.trace(d, generation_limit=gl)
+        res = eng.trace_wavefront(d, generation_limit=gl)
+        assert res.rows == want.shape[1], name
+        assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), name
+        for k in ("rays", "generations", "segments", "tie_rays", "untraceable_hits", "bad_w", "nan_rays",
+                  "limit_rays", "absorber_segments", "mirror_segments"):
+            assert res.counters[k] == ref.counters[k], (name, k)
+        assert np.array_equal(res.gen_counts, ref.gen_counts)
+        via = eng.trace(d, generation_limit=gl, method="wavefront", to_host=True)
+        assert np.array_equal(via.frame.numpy(), want, equal_nan=True), name
+        tiny = eng.trace_wavefront(d, generation_limit=gl, capacity=7, to_host=True)  # overflow -> exact retry
+        assert np.array_equal(tiny.frame.numpy(), want, equal_nan=True), name
+        sid = int(scene.leaf_sid[-1])
+        det = eng.trace_wavefront(d, generation_limit=gl, record="surface", detector_sid=sid)
+        assert np.array_equal(det.frame.cpu().numpy(), want[:, want[5] == sid], equal_nan=True), name
+    for seed in range(6):
+        scene, rays = su.random_scene_and_rays(300 + seed, n_rays=3000)
+        eng = pyrayt_b200.Engine(scene, device=0)
+        d = torch_mod.from_numpy(rays).cuda()
+        want, _ = oracle.trace(scene, rays, 14)
+        ev = []
+        res = eng.trace_wavefront(d, generation_limit=14, nearest_events=ev)
+        assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), seed
+        assert len(ev) == 15 and all(a.elapsed_time(b) >= 0 for a, b in ev)
+    # edge sizes
+    scene, rays, _, gl = load_case("thick_lens_zoo")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    for n in (0, 1, 255, 256, 257):
+        sub = np.ascontiguousarray(rays[:, :n])
+        want, _ = oracle.trace(scene, sub, gl)
+        res = eng.trace_wavefront(torch_mod.from_numpy(sub).cuda(), generation_limit=gl)
+        assert res.frame.shape == (15, want.shape[1])
+        assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), n
