@@ -52,3 +52,21 @@ def test_closed_form_left_deep_merge_equals_streaming_merge():
     """All sorted pairs over {-inf,-2,-1,1,2,3,+inf} for A, B, C and all 9 operation pairs."""
     bad, cases = emul.selfcheck_left_deep()
     assert cases == 9 * 28 ** 3 and bad == 0
+
+
+def test_random_scene_stress():
+    """600 more random scenes (random / tight / shrunk boxes, non-uniform scales, every primitive and
+    material): frames bit-equal to the oracle, every component.intersect slot equal."""
+    for seed in range(1000, 1600):
+        scene, rays = su.random_scene_and_rays(seed, n_rays=256)
+        want, octr = oracle.trace(scene, rays, 16)
+        got, ectr = emul.trace(scene, rays, 16)
+        assert np.array_equal(got, want, equal_nan=True), seed
+        assert ectr["generations"] == octr["generations"], seed
+        if seed % 6 == 0:
+            r = np.zeros((8, 64))
+            r[0:3], r[3], r[4:7] = rays[0:3, :64], 1, rays[4:7, :64]
+            for c in range(scene.n_components):
+                oh, osid = oracle.intersect(scene, c, r)
+                eh, esid = emul.intersect(scene, c, r)
+                assert np.array_equal(eh, oh) and np.array_equal(esid, osid), (seed, c)
