@@ -384,9 +384,38 @@ def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ra
     barrier()
     ms = max_over_ranks(t0.elapsed_time(t1)) / steps
     chk = float(h_frame[5, :1024].sum())  # touch the host result
-    return {"value": world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
-            "h2d_bytes_per_step": int(h_rays.numel() * 8), "d2h_bytes_per_step": int(frame_bytes),
-            "host_checksum": chk}
+    out = {"value": world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "h2d_bytes_per_step": int(h_rays.numel() * 8), "d2h_bytes_per_step": int(frame_bytes),
+           "host_checksum": chk}
+    del h_frame
+
+    # the same call chain when the user reads per-field spot statistics instead of the whole frame:
+    # host rays in, trace, read-out kernels on the device frame, a 9 x 17 table out
+    from pyrayt_b200 import analytics
+
+    det = float(engine.scene.leaf_sid[-1])
+    per_group = (world * n + 8) // 9
+
+    def step_readout():
+        dev_in.copy_(h_rays, non_blocking=True)
+        r = engine.trace(dev_in, generation_limit=G, record="all")
+        return analytics.spot_stats(r, per_group, 9, surface=det)
+
+    step_readout()
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(steps):
+        table = step_readout()
+    t1.record()
+    barrier()
+    ms2 = max_over_ranks(t0.elapsed_time(t1)) / steps
+    out["with_device_readout"] = {
+        "what": "host rays in -> trace -> analytics.spot_stats on the device frame -> 9 x 17 table out "
+                "(the frame is not copied)",
+        "value": world * n / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
+        "d2h_bytes_per_step": int(table.shape[0] * table.shape[1] * 8)}
+    return out
 
 
 if __name__ == "__main__":

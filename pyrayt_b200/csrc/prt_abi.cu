@@ -41,31 +41,7 @@ cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const 
                                long long* sid_out, double* normals, cudaStream_t st);
 }
 
-// mirrors prt::WaveArgs (prt_wavefront.cu)
-struct WaveArgsAbi {
-  const unsigned char* blob;
-  int blob_bytes;
-  int generation_limit;
-  int record_mode;
-  int g;
-  double ray_offset;
-  double detector_sid;
-  const double* rays;
-  long long n_rays, stride;
-  double* st;
-  int* flag;
-  double* hit_t;
-  int* hit_leaf;
-  int* blk_count;
-  long long* blk_base;
-  long long* alive;
-  long long* gen_off;
-  long long n_tiles;
-  double* frame;
-  long long frame_stride, capacity;
-  prt_counters* ctr;
-};
-extern "C" cudaError_t prt_launch_wavefront(WaveArgsAbi* a, int generic, cudaEvent_t* events, cudaStream_t st);
+extern "C" cudaError_t prt_launch_wavefront(prt::WaveArgs* a, int generic, cudaEvent_t* events, cudaStream_t st);
 
 struct prt_scene {
   int device = 0;
@@ -234,7 +210,7 @@ int prt_trace_wavefront(prt_scene* scene, const prt_params* p, const double* d_r
     return fail(PRT_ERR_INVALID, "workspace buffer missing");
   if (!ws->d_alive) return fail(PRT_ERR_INVALID, "workspace buffer missing");
   if (capacity < 0 || (capacity > 0 && !d_frame) || frame_stride < capacity) return fail(PRT_ERR_INVALID, "bad frame");
-  WaveArgsAbi a;
+  prt::WaveArgs a;
   std::memset(&a, 0, sizeof a);
   a.blob = scene->d_blob;
   a.blob_bytes = scene->blob_bytes;

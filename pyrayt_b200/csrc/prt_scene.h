@@ -104,4 +104,29 @@ struct TraceArgs {
   prt_counters* ctr;
 };
 
+// arguments of the wavefront driver (prt_wavefront.cu), filled by prt_trace_wavefront
+struct WaveArgs {
+  const unsigned char* blob;
+  int blob_bytes;
+  int generation_limit;
+  int record_mode;
+  int g;
+  double ray_offset;
+  double detector_sid;
+  const double* rays;
+  long long n_rays, stride;
+  double* st;  // rows p0,p1,p2,v0,v1,v2,nidx: st[k*n_rays + i]
+  int* flag;
+  double* hit_t;
+  int* hit_leaf;
+  int* blk_count;       // [2 * n_tiles] by generation parity
+  long long* blk_base;  // [2 * n_tiles]
+  long long* alive;    // [generation_limit + 1]: live rays entering generation g (alive[0] unused)
+  long long* gen_off;  // [generation_limit + 1]
+  long long n_tiles;
+  double* frame;
+  long long frame_stride, capacity;
+  prt_counters* ctr;
+};
+
 }  // namespace prt

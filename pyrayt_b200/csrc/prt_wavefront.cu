@@ -1,21 +1,25 @@
-// Wavefront form of the generation loop for large ray sets.
+// Wavefront form of the generation loop: one launch per generation, rows written in place.
 //
 // prt_trace (prt_kernels.cu) runs every generation of a ray inside one thread; it cannot know where a
 // row belongs in the (generation, id)-ordered frame, so rows go to a staging buffer and a second pass
-// moves them (240 B of HBM traffic per row), and its loop body needs ~170 registers.  Here one
-// generation is three launches over ray state kept in HBM:
+// moves them: 240 B of device memory and of HBM traffic per row.  Here the ray state lives in HBM and
+// the generations are separate launches of one kernel:
 //
-//   nearest  (A)  _st_propagate: nearest positive hit of every live ray; per-tile count of the rows
-//                 generation g will write.  Only position, direction and the skip hint are live:
-//                 the kernel fits in 128 registers without spilling.
-//   scan     (S)  exclusive scan of the tile counts; first frame row of generation g+1.
-//   interact (B)  _st_interact: material, new direction; the row is written straight to its final
-//                 frame position (first row of g + rows of lower tiles + rank inside the tile), the
-//                 state of surviving rays is written back.
+//   step g   finishes generation g-1 for every ray that hit something (_st_interact: material, new
+//            direction, the row, the new state) and starts generation g for every ray that goes on
+//            (_st_propagate: nearest hit), counting per tile the rows generation g will produce;
+//   scan g   turns those counts into frame positions (exclusive scan over the tiles, first row of
+//            generation g+1).
 //
-// All launches are enqueued at once; a generation with no live ray returns at once (device-side count
-// of survivors), so the host never synchronises inside a trace.  The per-ray arithmetic is the same
-// PRT_HD code as the single-kernel path (prt_device.cuh): frames are bit-identical.
+// Because step g+1 knows the exact position of every row of generation g, rows are written straight
+// to their final place: no staging buffer, no ordering pass.  All launches are enqueued at once; a
+// launch for a generation no ray reaches returns immediately (device-side count of survivors), so the
+// host never synchronises inside a trace.  The per-ray arithmetic is the same PRT_HD code as the
+// single-kernel path (prt_device.cuh): frames are bit-identical.
+//
+// Measured on config 4 (2^24 rays): 73.3 ms per trace against 70.9 ms for prt_trace + scan + gather:
+// the state round trip through HBM costs what the missing gather saves.  It is the path for ray sets
+// whose staging buffer + frame would not fit the device (Engine.trace(method="auto")).
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -34,30 +38,6 @@ constexpr int kWaveTile = PRT_WAVE_TILE;
 // per-ray flag word: bits 0-7 skip component + 1, bit 8 a tie was already counted, bit 9 dead
 constexpr int kFlagTie = 1 << 8, kFlagDead = 1 << 9;
 constexpr int kLeafDead = -2;  // hit_leaf: the ray took no step this generation
-
-struct WaveArgs {
-  const unsigned char* blob;
-  int blob_bytes;
-  int generation_limit;
-  int record_mode;
-  int g;
-  double ray_offset;
-  double detector_sid;
-  const double* rays;
-  long long n_rays, stride;
-  double* st;  // rows p0,p1,p2,v0,v1,v2,nidx: st[k*n_rays + i]
-  int* flag;
-  double* hit_t;
-  int* hit_leaf;
-  int* blk_count;       // [2 * n_tiles] by generation parity
-  long long* blk_base;  // [2 * n_tiles]
-  long long* alive;    // [generation_limit + 1]: live rays entering generation g (alive[0] unused)
-  long long* gen_off;  // [generation_limit + 1]
-  long long n_tiles;
-  double* frame;
-  long long frame_stride, capacity;
-  prt_counters* ctr;
-};
 
 __device__ __forceinline__ void stage_blob(unsigned char* s_blob, const unsigned char* blob, int blob_bytes) {
   const int words = blob_bytes / 8;
