@@ -102,8 +102,7 @@ PRT_HD_CALL double slow_div(double a, double b) { return a / b; }
 
 PRT_HD double div_by(double a, const Rcp& R) {
   if (exp_of(a) - kExpLo < R.lim) return div_fast(a, R);
-  if (a == 0.0 && R.lim != 0u) return a * R.r;  // signed zero, like a / b
-  return slow_div(a, R.b);                      // tiny, huge, inf, NaN or an unsafe denominator
+  return slow_div(a, R.b);  // zero, tiny, huge, inf, NaN or an unsafe denominator: one shared IEEE division
 }
 
 // Two / three quotients by the same denominator: the 3-instruction form is computed for all of them
@@ -871,6 +870,10 @@ PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int gen
   const Rcp rvn = make_rcp(vn);
   div_by3(r.v0, r.v1, r.v2, rvn, o.t0n, o.t1n, o.t2n);
   bool goes_on = true;
+  // mirrors and glasses need the surface normal (one call site: the primitive switch is large)
+  double n0 = 0, n1 = 0, n2 = 0;
+  if (L.mat == PRT_MAT_MIRROR || L.mat == PRT_MAT_GLASS_CONST || L.mat == PRT_MAT_GLASS_SELLMEIER)
+    world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
   if (L.mat == PRT_MAT_ABSORBER) {  // materials.py:47-50
     o.nv0 = 0;
     o.nv1 = 0;
@@ -878,9 +881,7 @@ PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int gen
     goes_on = false;  // recorded now, dead next generation (zero direction)
     c.w1 |= kCtrAbs;
   } else if (L.mat == PRT_MAT_MIRROR) {  // materials.py:58-62, operations.py:105-107
-    double n0, n1, n2;
     c.w1 += 1u;
-    world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
     const double dots = r.v0 * n0 + r.v1 * n1 + r.v2 * n2;
     o.nv0 = r.v0 - 2 * n0 * dots;
     o.nv1 = r.v1 - 2 * n1 * dots;
@@ -888,8 +889,6 @@ PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int gen
     o.skip = leaves_for_good(sc, L, o.nv0 * n0 + o.nv1 * n1 + o.nv2 * n2);
   } else if (L.mat == PRT_MAT_GLASS_CONST || L.mat == PRT_MAT_GLASS_SELLMEIER) {
     // materials.py:70-75,:112-118,:136-145 ; operations.py:110-162
-    double n0, n1, n2;
-    world_normal(L, o.e0, o.e1, o.e2, n0, n1, n2);
     const double u0 = o.t0n, u1 = o.t1n, u2 = o.t2n;
     const double cp = u0 * n0 + u1 * n1 + u2 * n2;
     const bool exiting = cp > 0;  // leaving the glass always enters n = 1 (operations.py:134)
