@@ -232,6 +232,26 @@ int prt_gather_frame(const prt_records* records, int32_t generation_limit, const
                      double* frame, int64_t frame_stride, int32_t layout, void* cuda_stream);
 
 /*
+ * Lean device -> host transfer of a frame.  Five of the fifteen columns can be rebuilt on the host from
+ * the input rays: generation (from the row position), intensity, wavelength and id (copies of the ray's
+ * input values) and surface (a small integer).  prt_frame_pack writes one word per row,
+ * (index of the ray in d_rays) << 24 | (surface id + 1), after checking row by row that the frame holds
+ * exactly what the host will rebuild (ids consecutive from d_rays' first id, intensity / wavelength
+ * bit-equal to the ray's, surface id an integer in [-1, 2^24 - 2]); *d_bad receives the number of rows
+ * that failed -- if it is not zero the caller must copy all fifteen columns instead.
+ * prt_host_expand_frame (host code, `threads` worker threads) then fills columns 0, 1, 2, 4, 5 of a host
+ * frame from the packed words, the per-generation row offsets and host copies of rows 8, 9, 10 and 12 of the RaySet
+ * (generation, intensity, wavelength, id; each n_rays long), while the
+ * other ten columns are copied as usual: 88 instead of 120 bytes per row cross the bus.
+ */
+int prt_frame_pack(const double* d_frame, int64_t rows, int64_t frame_stride, const double* d_rays, int64_t n_rays,
+                   int64_t ray_stride, uint64_t* d_packed, uint64_t* d_bad, void* cuda_stream);
+int prt_host_expand_frame(const uint64_t* h_packed, int64_t rows, const int64_t* h_gen_offsets,
+                          int32_t generation_limit, const double* h_ray_generation, const double* h_ray_intensity,
+                          const double* h_ray_wavelength, const double* h_ray_id, double* h_frame,
+                          int64_t frame_stride, int32_t threads);
+
+/*
  * component.intersect(rays): d_rays is (2,4,N) like the reference (row k of ray i
  * at d_rays[k*n + i]); writes hits (m,N) ascending with +inf padding and the
  * surface ids (m,N) exactly as the reference returns them -- the ids carried by

@@ -35,7 +35,7 @@ EXPORTS = (
     "prt_abi_version", "prt_last_error", "prt_tile_rays", "prt_scene_create", "prt_scene_destroy",
     "prt_scene_n_leaves", "prt_trace", "prt_scan_runs", "prt_gather_frame", "prt_intersect",
     "prt_generate_source", "prt_fp64_probe", "prt_nearest_hit", "prt_scene_update",
-    "prt_render_hit", "prt_wave_tile", "prt_trace_wavefront", "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
+    "prt_render_hit", "prt_wave_tile", "prt_trace_wavefront", "prt_frame_pack", "prt_host_expand_frame", "prt_spot_moments", "prt_spot_centers", "prt_axis_table_blocks", "prt_axis_table",
 )
 
 
@@ -141,6 +141,10 @@ def load():
     lib.prt_axis_table_blocks.argtypes = [i64]
     lib.prt_axis_table.restype = ctypes.c_int
     lib.prt_axis_table.argtypes = [vp, i64, i64, i32, f64, i64, i64, vp, vp, vp, vp, i64, i64, vp]
+    lib.prt_frame_pack.restype = ctypes.c_int
+    lib.prt_frame_pack.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp, vp]
+    lib.prt_host_expand_frame.restype = ctypes.c_int
+    lib.prt_host_expand_frame.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, i64, i32]
     lib.prt_fp64_probe.restype = ctypes.c_int
     lib.prt_fp64_probe.argtypes = [vp, i32, i32, vp]
     if lib.prt_abi_version() != ABI_VERSION:

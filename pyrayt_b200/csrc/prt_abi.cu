@@ -5,7 +5,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pyrayt_b200.h"
@@ -37,6 +39,12 @@ cudaError_t prt_launch_axis_table(const double* frame, long long rows, long long
                                   long long first_id, long long gen0_rows, int* block_count, long long* block_base,
                                   long long* total, double* table, long long table_stride, long long table_capacity,
                                   cudaStream_t st);
+cudaError_t prt_launch_frame_pack(const double* frame, long long rows, long long stride, const double* rays,
+                                  long long n_rays, long long ray_stride, unsigned long long* packed,
+                                  unsigned long long* bad, cudaStream_t st);
+void prt_host_expand_rows(const uint64_t* packed, int64_t r0, int64_t r1, const int64_t* gen_off, int32_t generations,
+                          const double* r_gen, const double* r_int, const double* r_wl, const double* r_id,
+                          double* frame, int64_t frame_stride);
 cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const double* rays, long long n, double* t_out,
                                long long* sid_out, double* normals, cudaStream_t st);
 }
@@ -313,6 +321,43 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
   if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
   cudaError_t e = prt_launch_source(src, d_rays, n_rays, ray_stride, first_index, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "source kernel launch");
+  return PRT_OK;
+}
+
+int prt_frame_pack(const double* d_frame, int64_t rows, int64_t frame_stride, const double* d_rays, int64_t n_rays,
+                   int64_t ray_stride, uint64_t* d_packed, uint64_t* d_bad, void* cuda_stream) {
+  if (rows < 0 || (rows > 0 && (!d_frame || !d_packed)) || frame_stride < rows) return fail(PRT_ERR_INVALID, "bad frame");
+  if (!d_bad) return fail(PRT_ERR_INVALID, "d_bad is NULL");
+  if (rows > 0 && (n_rays < 1 || !d_rays || ray_stride < n_rays)) return fail(PRT_ERR_INVALID, "bad ray buffer");
+  cudaError_t e = prt_launch_frame_pack(d_frame, rows, frame_stride, d_rays, n_rays, ray_stride,
+                                        reinterpret_cast<unsigned long long*>(d_packed),
+                                        reinterpret_cast<unsigned long long*>(d_bad), (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "frame pack launch");
+  return PRT_OK;
+}
+
+int prt_host_expand_frame(const uint64_t* h_packed, int64_t rows, const int64_t* h_gen_offsets,
+                          int32_t generation_limit, const double* h_ray_generation, const double* h_ray_intensity,
+                          const double* h_ray_wavelength, const double* h_ray_id, double* h_frame,
+                          int64_t frame_stride, int32_t threads) {
+  if (rows < 0 || generation_limit < 1) return fail(PRT_ERR_INVALID, "bad arguments");
+  if (rows == 0) return PRT_OK;
+  if (!h_packed || !h_gen_offsets || !h_ray_generation || !h_ray_intensity || !h_ray_wavelength || !h_ray_id ||
+      !h_frame || frame_stride < rows)
+    return fail(PRT_ERR_INVALID, "null or short buffer");
+  if (h_gen_offsets[0] != 0 || h_gen_offsets[generation_limit] != rows)
+    return fail(PRT_ERR_INVALID, "generation offsets do not cover the frame");
+  int t = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  t = std::max(1, std::min<int>(t, (int)std::min<int64_t>(64, (rows + 65535) / 65536)));
+  std::vector<std::thread> pool;
+  const int64_t chunk = (rows + t - 1) / t;
+  for (int k = 0; k < t; ++k) {
+    const int64_t r0 = (int64_t)k * chunk, r1 = std::min<int64_t>(rows, r0 + chunk);
+    if (r0 >= r1) break;
+    pool.emplace_back(prt_host_expand_rows, h_packed, r0, r1, h_gen_offsets, generation_limit, h_ray_generation,
+                      h_ray_intensity, h_ray_wavelength, h_ray_id, h_frame, frame_stride);
+  }
+  for (auto& th : pool) th.join();
   return PRT_OK;
 }
 

@@ -54,6 +54,8 @@ class Engine:
         self.n_leaves = scene.n_leaves
         self.rows_per_ray_hint = 4.0
         self._ws = {}
+        self._pin = {}
+        self.host_threads = 0  # worker threads of the host-side column rebuild (0 = all hardware threads)
 
     def close(self) -> None:
         if getattr(self, "_handle", None):
@@ -88,11 +90,13 @@ class Engine:
         if self._torch.cuda.is_available():
             self._torch.cuda.synchronize(self.device)
         self._ws.clear()
+        self._pin.clear()
 
     # ------------------------------------------------------------------ trace
     def trace(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
               detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
-              host_frame=None, zero_copy: bool = False, k1_events=None, method: str = "auto") -> TraceResult:
+              host_frame=None, zero_copy: bool = False, k1_events=None, method: str = "auto", host_rays=None,
+              lean="auto") -> TraceResult:
         """Trace a device RaySet.
 
         method: "single" = one kernel for all generations + ordering pass (staging buffer and frame: 240 B
@@ -101,8 +105,10 @@ class Engine:
         staging + frame would not fit the device.
 
         d_rays: torch float64 CUDA tensor (13, N) in the reference RaySet layout.
-        to_host: return the frame in pinned host memory (one D2H copy, or with
-        ``zero_copy`` the gather kernel writes straight into the pinned buffer).
+        to_host: return the frame in pinned host memory (``lean``: "auto" = frames of 2^21 rows or more
+        use the lean transfer that rebuilds five columns on the host, see _frame_to_host; True / False force
+        it; ``host_rays``: pinned host copy of d_rays if the caller has one; with ``zero_copy`` the gather
+        kernel writes straight into the pinned buffer instead).
         k1_events: optional (start, end) torch CUDA events; ``end`` is recorded right after the
         trace kernel so a caller can time that kernel alone on the launching stream.
         """
@@ -121,7 +127,7 @@ class Engine:
             if method == "wavefront" or 2 * 8 * _lib.FRAME_COLS * rows_guess > 0.8 * total:
                 return self.trace_wavefront(d_rays, generation_limit=G, ray_offset=ray_offset, record=record,
                                             detector_sid=detector_sid, capacity=capacity, to_host=to_host,
-                                            host_frame=host_frame)
+                                            host_frame=host_frame, host_rays=host_rays, lean=lean)
         n_tiles = max(1, (n + self.tile - 1) // self.tile)
         launches = 0
         with torch.cuda.device(self.device):
@@ -168,7 +174,7 @@ class Engine:
             if n > 0:
                 self.rows_per_ray_hint = max(self.rows_per_ray_hint, rows / n)
             gen_counts = np.diff(goff).astype(np.int64)
-            frame = self._gather(rec, G, gen_off, rows, to_host, host_frame, zero_copy)
+            frame = self._gather(rec, G, gen_off, rows, to_host, host_frame, zero_copy, goff, d_rays, host_rays, lean)
             launches += 1 if rows else 0
             return TraceResult(frame, rows, counters, gen_counts, launches, self.n_leaves)
 
@@ -177,7 +183,7 @@ class Engine:
 
     def trace_wavefront(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
                         detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
-                        host_frame=None, nearest_events=None) -> TraceResult:
+                        host_frame=None, nearest_events=None, host_rays=None, lean="auto") -> TraceResult:
         """Same result as trace(), computed generation by generation (prt_trace_wavefront): every row is
         written straight to its final frame position, so there is no staging buffer and no ordering
         pass.  The device frame is a (15, rows) view of a (15, capacity) buffer.
@@ -241,12 +247,8 @@ class Engine:
             launches = 2 * G + 1
             out = frame[:, :rows]
             if to_host:
-                pinned = host_frame if host_frame is not None else torch.empty(
-                    (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
-                for c in range(_lib.FRAME_COLS):  # column by column: each one is contiguous on both sides
-                    pinned[c, :rows].copy_(out[c], non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                out = pinned[:, :rows]
+                out = self._frame_to_host(frame, rows, goff, d_rays, host_frame, host_rays, lean) if rows else \
+                    torch.empty((_lib.FRAME_COLS, 0), dtype=torch.float64)
             return TraceResult(out, rows, counters, gen_counts, launches, self.n_leaves)
 
     # ------------------------------------------------------------------ many small traces (N4)
@@ -349,7 +351,74 @@ class Engine:
         st["h_meta"].copy_(meta, non_blocking=True)
         st["h_frame"].copy_(st["frame"], non_blocking=True)
 
-    def _gather(self, rec, G, gen_off, rows, to_host, host_frame, zero_copy):
+    # ------------------------------------------------------------------ device frame -> pinned host frame
+    LEAN_MIN_ROWS = 1 << 21
+
+    def _pinned(self, key, numel, dtype):
+        """Grow-only pinned host buffers (kept apart from the device workspace)."""
+        t = self._pin.get(key)
+        if t is not None and t.numel() >= numel and t.dtype == dtype:
+            return t
+        self._pin[key] = None
+        t = self._torch.empty(int(numel), dtype=dtype, pin_memory=True)
+        self._pin[key] = t
+        return t
+
+    def _frame_to_host(self, frame, rows, goff, d_rays, host_frame=None, host_rays=None, lean="auto"):
+        """Copy a device frame (15, >= rows; contiguous columns) into pinned host memory.
+
+        Large frames take the lean transfer (csrc/prt_transfer.cu): five columns are rebuilt on the host
+        from the input rays while the other ten stream over the bus.  host_rays: pinned host copy of the
+        (13, n) RaySet if the caller has one (else the four rows needed are copied back).
+        """
+        torch = self._torch
+        out = host_frame if host_frame is not None else torch.empty(
+            (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
+        assert out.shape[0] == _lib.FRAME_COLS and out.shape[1] >= rows and out.stride(1) == 1
+        stream = torch.cuda.current_stream(self.device)
+        n = int(d_rays.shape[1]) if d_rays is not None else 0
+        use_lean = n > 0 and (lean is True or (lean == "auto" and rows >= self.LEAN_MIN_ROWS))
+        if not use_lean:
+            for c in range(_lib.FRAME_COLS):  # column by column: contiguous on both sides whatever the strides
+                out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
+            stream.synchronize()
+            return out[:, :rows]
+        packed = torch.empty(rows, dtype=torch.int64, device=self._dev())
+        bad = self._buf("pack_bad", 1, torch.int64)
+        _lib.check(self.lib.prt_frame_pack(frame.data_ptr(), rows, int(frame.stride(0)), d_rays.data_ptr(), n,
+                                           int(d_rays.stride(0)), packed.data_ptr(), bad.data_ptr(), self._stream()),
+                   "prt_frame_pack")
+        h_packed = self._pinned("h_packed", rows, torch.int64)
+        h_bad = self._pinned("h_bad", 1, torch.int64)
+        h_packed[:rows].copy_(packed, non_blocking=True)
+        h_bad.copy_(bad, non_blocking=True)
+        if host_rays is None:
+            h4 = self._pinned("h_ray_rows", 4 * n, torch.float64).view(-1)[: 4 * n].view(4, n)
+            for k, row in enumerate((8, 9, 10, 12)):
+                h4[k].copy_(d_rays[row], non_blocking=True)
+            ray_rows = [h4[k] for k in range(4)]
+        else:
+            ray_rows = [host_rays[row] for row in (8, 9, 10, 12)]
+            assert all(r.stride(0) == 1 and r.dtype == torch.float64 for r in ray_rows)
+        arrived = torch.cuda.Event()
+        arrived.record(stream)
+        for c in (3, 6, 7, 8, 9, 10, 11, 12, 13, 14):  # the columns only the device knows
+            out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
+        arrived.synchronize()
+        if int(h_bad[0]) == 0:
+            goff = np.ascontiguousarray(goff, dtype=np.int64)
+            _lib.check(self.lib.prt_host_expand_frame(
+                h_packed.data_ptr(), rows, goff.ctypes.data_as(ctypes.c_void_p), len(goff) - 1,
+                ray_rows[0].data_ptr(), ray_rows[1].data_ptr(), ray_rows[2].data_ptr(), ray_rows[3].data_ptr(),
+                out.data_ptr(), int(out.stride(0)), int(self.host_threads)), "prt_host_expand_frame")
+        else:  # some row does not verify (ids not consecutive, exotic surface ids): copy the five columns too
+            for c in (0, 1, 2, 4, 5):
+                out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
+        stream.synchronize()
+        return out[:, :rows]
+
+    def _gather(self, rec, G, gen_off, rows, to_host, host_frame, zero_copy, goff=None, d_rays=None, host_rays=None,
+                lean="auto"):
         torch = self._torch
         if rows == 0:
             if to_host:
@@ -368,11 +437,7 @@ class Engine:
                                              self._stream()), "prt_gather_frame")
         if not to_host:
             return frame
-        out = host_frame if host_frame is not None else torch.empty(
-            (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
-        out[:, :rows].copy_(frame, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return out[:, :rows]
+        return self._frame_to_host(frame, rows, goff, d_rays, host_frame, host_rays, lean)
 
     def _counters(self, ctr) -> dict:
         host = ctr.cpu()
