@@ -13,8 +13,12 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstring>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/pyrayt_b200.h"
 
@@ -33,7 +37,8 @@ __global__ void __launch_bounds__(256) frame_pack_kernel(const double* __restric
     const double rel = id - id0;
     const long long idx = (rel >= 0.0 && rel < 1099511627776.0) ? (long long)rel : -1;  // < 2^40
     const long long s = (sid >= -1.0 && sid < 16777215.0) ? (long long)sid : -2;
-    bool ok = idx >= 0 && idx < n_rays && (double)idx == rel && s >= -1 && (double)s == sid;
+    // (the host rebuilds id as id0 + index: both directions of that identity are checked)
+    bool ok = idx >= 0 && idx < n_rays && (double)idx == rel && id0 + (double)idx == id && s >= -1 && (double)s == sid;
     if (ok) {
       ok = rays[12 * ray_stride + idx] == id && rays[9 * ray_stride + idx] == frame[1 * stride + r] &&
            rays[10 * ray_stride + idx] == frame[2 * stride + r];
@@ -46,6 +51,18 @@ __global__ void __launch_bounds__(256) frame_pack_kernel(const double* __restric
 }
 
 }  // namespace prt
+
+// The rebuilt columns are written once and not read again by these threads: store them around the
+// cache (no read-for-ownership of 12 GB of destination lines while the DMA engine writes next to them).
+static inline void store_stream(double* p, double v) {
+#if defined(__x86_64__)
+  long long bits;
+  std::memcpy(&bits, &v, 8);
+  _mm_stream_si64(reinterpret_cast<long long*>(p), bits);
+#else
+  *p = v;
+#endif
+}
 
 extern "C" {
 
@@ -69,6 +86,7 @@ void prt_host_expand_rows(const uint64_t* packed, int64_t r0, int64_t r1, const 
   double* f_wl = frame + 2 * frame_stride;
   double* f_id = frame + 4 * frame_stride;
   double* f_sid = frame + 5 * frame_stride;
+  const double id0 = r_id[0];
   // generation of row r0: last g with gen_off[g] <= r0
   int g = (int)(std::upper_bound(gen_off, gen_off + generations + 1, r0) - gen_off) - 1;
   int64_t r = r0;
@@ -78,13 +96,16 @@ void prt_host_expand_rows(const uint64_t* packed, int64_t r0, int64_t r1, const 
     for (; r < end; ++r) {
       const uint64_t p = packed[r];
       const int64_t idx = (int64_t)(p >> 24);
-      f_gen[r] = (g == 0) ? r_gen[idx] : (double)g;  // pyrayt/_pyrayt.py:440-441
-      f_int[r] = r_int[idx];
-      f_wl[r] = r_wl[idx];
-      f_id[r] = r_id[idx];
-      f_sid[r] = (double)((int64_t)(p & 0xffffffu) - 1);
+      store_stream(f_gen + r, (g == 0) ? r_gen[idx] : (double)g);  // pyrayt/_pyrayt.py:440-441
+      store_stream(f_int + r, r_int[idx]);
+      store_stream(f_wl + r, r_wl[idx]);
+      store_stream(f_id + r, id0 + (double)idx);  // ids are consecutive (verified by the pack kernel)
+      store_stream(f_sid + r, (double)((int64_t)(p & 0xffffffu) - 1));
     }
   }
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
 }
 
 }  // extern "C"
