@@ -7,6 +7,7 @@ path: constructing an Engine without a CUDA device raises.
 from __future__ import annotations
 
 import ctypes
+import time
 from dataclasses import dataclass
 from typing import Optional
 
@@ -55,6 +56,8 @@ class Engine:
         self.rows_per_ray_hint = 4.0
         self._ws = {}
         self._pin = {}
+        self.last_transfer = None  # "lean" / "full": how the last host frame crossed the bus
+        self._xfer_ms_per_row = {}  # measured once per kind of large host transfer ("lean" / "full")
         self.host_threads = 0  # worker threads of the host-side column rebuild (0 = all hardware threads)
 
     def close(self) -> None:
@@ -367,9 +370,12 @@ class Engine:
     def _frame_to_host(self, frame, rows, goff, d_rays, host_frame=None, host_rays=None, lean="auto"):
         """Copy a device frame (15, >= rows; contiguous columns) into pinned host memory.
 
-        Large frames take the lean transfer (csrc/prt_transfer.cu): five columns are rebuilt on the host
-        from the input rays while the other ten stream over the bus.  host_rays: pinned host copy of the
-        (13, n) RaySet if the caller has one (else the four rows needed are copied back).
+        Large frames can take the lean transfer (csrc/prt_transfer.cu): five columns are rebuilt on the
+        host from the input rays while the other ten stream over the bus.  Whether that beats copying all
+        fifteen depends on the host (cores per GPU, memory bandwidth left beside the DMA traffic), so with
+        lean="auto" an engine times its first large transfer of each kind and keeps the faster one.
+        host_rays: pinned host copy of the (13, n) RaySet if the caller has one (else the four rows needed
+        are copied back).
         """
         torch = self._torch
         out = host_frame if host_frame is not None else torch.empty(
@@ -377,44 +383,60 @@ class Engine:
         assert out.shape[0] == _lib.FRAME_COLS and out.shape[1] >= rows and out.stride(1) == 1
         stream = torch.cuda.current_stream(self.device)
         n = int(d_rays.shape[1]) if d_rays is not None else 0
-        use_lean = n > 0 and (lean is True or (lean == "auto" and rows >= self.LEAN_MIN_ROWS))
-        if not use_lean:
+        large = n > 0 and rows >= self.LEAN_MIN_ROWS
+        calibrating = False
+        if lean == "auto" and large:
+            untried = [m for m in ("lean", "full") if m not in self._xfer_ms_per_row]
+            calibrating = bool(untried)
+            mode = untried[0] if untried else min(self._xfer_ms_per_row, key=self._xfer_ms_per_row.get)
+        else:
+            mode = "lean" if (lean is True and n > 0) else "full"
+        self.last_transfer = mode
+        if mode == "lean":  # buffers first, so that a calibration run does not time their allocation
+            packed = torch.empty(rows, dtype=torch.int64, device=self._dev())
+            bad = self._buf("pack_bad", 1, torch.int64)
+            h_packed = self._pinned("h_packed", rows, torch.int64)
+            h_bad = self._pinned("h_bad", 1, torch.int64)
+            if host_rays is None:
+                h4 = self._pinned("h_ray_rows", 4 * n, torch.float64).view(-1)[: 4 * n].view(4, n)
+        if calibrating:
+            stream.synchronize()
+            t_begin = time.perf_counter()
+        if mode == "full":
             for c in range(_lib.FRAME_COLS):  # column by column: contiguous on both sides whatever the strides
                 out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
             stream.synchronize()
-            return out[:, :rows]
-        packed = torch.empty(rows, dtype=torch.int64, device=self._dev())
-        bad = self._buf("pack_bad", 1, torch.int64)
-        _lib.check(self.lib.prt_frame_pack(frame.data_ptr(), rows, int(frame.stride(0)), d_rays.data_ptr(), n,
-                                           int(d_rays.stride(0)), packed.data_ptr(), bad.data_ptr(), self._stream()),
-                   "prt_frame_pack")
-        h_packed = self._pinned("h_packed", rows, torch.int64)
-        h_bad = self._pinned("h_bad", 1, torch.int64)
-        h_packed[:rows].copy_(packed, non_blocking=True)
-        h_bad.copy_(bad, non_blocking=True)
-        if host_rays is None:
-            h4 = self._pinned("h_ray_rows", 4 * n, torch.float64).view(-1)[: 4 * n].view(4, n)
-            for k, row in enumerate((8, 9, 10, 12)):
-                h4[k].copy_(d_rays[row], non_blocking=True)
-            ray_rows = [h4[k] for k in range(4)]
         else:
-            ray_rows = [host_rays[row] for row in (8, 9, 10, 12)]
-            assert all(r.stride(0) == 1 and r.dtype == torch.float64 for r in ray_rows)
-        arrived = torch.cuda.Event()
-        arrived.record(stream)
-        for c in (3, 6, 7, 8, 9, 10, 11, 12, 13, 14):  # the columns only the device knows
-            out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
-        arrived.synchronize()
-        if int(h_bad[0]) == 0:
-            goff = np.ascontiguousarray(goff, dtype=np.int64)
-            _lib.check(self.lib.prt_host_expand_frame(
-                h_packed.data_ptr(), rows, goff.ctypes.data_as(ctypes.c_void_p), len(goff) - 1,
-                ray_rows[0].data_ptr(), ray_rows[1].data_ptr(), ray_rows[2].data_ptr(), ray_rows[3].data_ptr(),
-                out.data_ptr(), int(out.stride(0)), int(self.host_threads)), "prt_host_expand_frame")
-        else:  # some row does not verify (ids not consecutive, exotic surface ids): copy the five columns too
-            for c in (0, 1, 2, 4, 5):
+            _lib.check(self.lib.prt_frame_pack(frame.data_ptr(), rows, int(frame.stride(0)), d_rays.data_ptr(), n,
+                                               int(d_rays.stride(0)), packed.data_ptr(), bad.data_ptr(),
+                                               self._stream()), "prt_frame_pack")
+            h_packed[:rows].copy_(packed, non_blocking=True)
+            h_bad.copy_(bad, non_blocking=True)
+            if host_rays is None:
+                for k, row in enumerate((8, 9, 10, 12)):
+                    h4[k].copy_(d_rays[row], non_blocking=True)
+                ray_rows = [h4[k] for k in range(4)]
+            else:
+                ray_rows = [host_rays[row] for row in (8, 9, 10, 12)]
+                assert all(r.stride(0) == 1 and r.dtype == torch.float64 for r in ray_rows)
+            arrived = torch.cuda.Event()
+            arrived.record(stream)
+            for c in (3, 6, 7, 8, 9, 10, 11, 12, 13, 14):  # the columns only the device knows
                 out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
-        stream.synchronize()
+            arrived.synchronize()
+            if int(h_bad[0]) == 0:
+                goff = np.ascontiguousarray(goff, dtype=np.int64)
+                _lib.check(self.lib.prt_host_expand_frame(
+                    h_packed.data_ptr(), rows, goff.ctypes.data_as(ctypes.c_void_p), len(goff) - 1,
+                    ray_rows[0].data_ptr(), ray_rows[1].data_ptr(), ray_rows[2].data_ptr(), ray_rows[3].data_ptr(),
+                    out.data_ptr(), int(out.stride(0)), int(self.host_threads)), "prt_host_expand_frame")
+            else:  # some row does not verify (ids not consecutive, exotic surface ids): copy the five columns too
+                for c in (0, 1, 2, 4, 5):
+                    out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
+                self.last_transfer = "full"
+            stream.synchronize()
+        if calibrating:
+            self._xfer_ms_per_row[mode] = 1e3 * (time.perf_counter() - t_begin) / rows
         return out[:, :rows]
 
     def _gather(self, rec, G, gen_off, rows, to_host, host_frame, zero_copy, goff=None, d_rays=None, host_rays=None,
