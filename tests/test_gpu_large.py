@@ -109,6 +109,50 @@ def test_config4_full_size_properties(torch_mod):
     torch.cuda.empty_cache()
 
 
+def test_config5_full_size_properties_wavefront(torch_mod):
+    """BASELINE config 5 at its per-GPU size (2^25 rays, paraboloid + cuboid mirrors + TIR pipe), traced by
+    the wavefront driver (rows written in place): order, per-ray generation prefixes, strided oracle sample,
+    and the same frame as the single-kernel driver on the first 2^20 rays."""
+    from oracle import oracle, sources_np
+
+    torch = torch_mod
+    wl, eng = _engine("config5")
+    n = wl.n_rays
+    d_rays = wl.source.generate(n, device=0)
+    res = eng.trace_wavefront(d_rays, generation_limit=wl.generation_limit)
+    f = res.frame
+    assert res.rows == f.shape[1] == res.counters["segments"] and res.counters["rows_dropped"] == 0
+    assert res.rows / n >= 8.0  # SURVEY 8(d): the scene must average >= 8 segments per ray
+    gen, rid = f[0], f[4]
+    for lo in range(0, res.rows - 1, 1 << 27):  # (chunked: the key tensor of 4 x 10^8 rows is 3 GB)
+        hi = min(res.rows, lo + (1 << 27) + 1)
+        key = gen[lo:hi] * float(1 << 26) + rid[lo:hi]
+        assert bool((key[1:] > key[:-1]).all())
+        del key
+    gc = res.gen_counts
+    assert np.all(np.diff(gc) <= 0) and gc.sum() == res.rows
+    k = torch.bincount(rid.to(torch.int64), minlength=n)
+    gs = torch.zeros(n, dtype=torch.float64, device=f.device).index_add_(0, rid.to(torch.int64), gen)
+    assert bool((gs == (k * (k - 1) / 2).to(torch.float64)).all())
+    del k, gs
+    idx = np.arange(0, n, n // 1024)
+    h = np.hstack([sources_np.from_source(wl.source, 1, first_index=int(i)) for i in idx])
+    want, _ = oracle.trace(wl.scene(), h, wl.generation_limit, threads=THREADS)
+    sel = torch.isin(rid, torch.from_numpy(idx.astype(np.float64)).to(f.device))
+    assert np.array_equal(f[:, sel].cpu().numpy(), want, equal_nan=True)
+    del sel, f, res
+    torch.cuda.empty_cache()
+    m = 1 << 20
+    a = eng.trace(d_rays[:, :m].contiguous(), generation_limit=wl.generation_limit, method="single")
+    b = eng.trace(d_rays[:, :m].contiguous(), generation_limit=wl.generation_limit, method="wavefront")
+    assert a.rows == b.rows and bool((a.frame == b.frame).all())
+    assert all(a.counters[key] == b.counters[key] for key in ("generations", "segments", "mirror_segments",
+                                                              "absorber_segments", "limit_rays", "tie_rays"))
+    del a, b
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+
+
 def test_sharded_ranges_reassemble_the_monolithic_frame(torch_mod):
     """tracing ray-index ranges separately and placing the blocks by the all-gathered
     counts gives the single-GPU frame bit for bit."""
