@@ -656,12 +656,41 @@ PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
   cl = take ? leaf : cl;
 }
 
+// The ray's dominant axis, for a two-instruction version of the proven-box pruning: along one axis the
+// far face of a box gives an upper bound of the exit distance b1 and the near face a lower bound of the
+// entry distance b0, so "far < -margin" or "near > best + margin" (with twice the margin, which swallows
+// the rounding of the unguarded product) implies the exact test below would prune as well.
+struct DomAxis {
+  double o, r;  // origin coordinate and reciprocal direction along the axis
+  int near;     // index of the near face in a 6-span box (the far face is near ^ 1); < 0: quick test not usable
+};
+
+PRT_HD DomAxis make_dom_axis(double p0, double p1, double p2, double v0, double v1, double v2, const RayInv& inv,
+                             bool small_boxes) {
+  const double a0 = fabs(v0), a1 = fabs(v1), a2 = fabs(v2);
+  const int k = (a0 >= a1) ? ((a0 >= a2) ? 0 : 2) : ((a1 >= a2) ? 1 : 2);
+  const double a = (k == 0) ? a0 : ((k == 1) ? a1 : a2);
+  DomAxis d;
+  d.o = (k == 0) ? p0 : ((k == 1) ? p1 : p2);
+  d.r = (k == 0) ? inv.r0 : ((k == 1) ? inv.r1 : inv.r2);
+  const int s = (inv.bits >> (3 + k)) & 1;
+  // with |o|, |face| <= 1e6 and 1/4 <= |d| <= 4 the product below is off by < 1e-8, well inside the doubled margin
+  d.near = (small_boxes && fabs(d.o) <= 1e6 && a >= 0.25 && a <= 4.0) ? 2 * k + s : -1;
+  return d;
+}
+
 // shapes 2/3: (A op1 B) [op2 C] with their bounding boxes (csg.py:118-160 for a left-deep tree)
 PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double p1, double p2, double v0, double v1,
-                           double v2, const RayInv& inv, double best_t, double& ct, int& cl, bool& tie) {
+                           double v2, const RayInv& inv, const DomAxis& dom, double best_t, double& ct, int& cl,
+                           bool& tie) {
   ct = PRT_INF;
   cl = -1;
   const int shape = C.shape;
+  if (((C.flags & 1) != 0) & (dom.near >= 0)) {
+    const double t_far = (C.root_box[dom.near ^ 1] - dom.o) * dom.r;
+    const double t_near = (C.root_box[dom.near] - dom.o) * dom.r;
+    if ((t_far < -2 * kCullMargin) | (t_near > best_t + 2 * kCullMargin)) return;
+  }
   double b0, b1;
   cube_hits(C.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
   if (!(b0 < PRT_INF)) return;  // csg.py:126-133
@@ -763,6 +792,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
   best_t = PRT_INF;
   best_leaf = -1;
   const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
+  const DomAxis dom = make_dom_axis(p0, p1, p2, v0, v1, v2, inv, (sc.h->flags & 4) != 0);
   const int nc = sc.h->n_components;
   {
     for (int c = 0; c < nc; ++c) {
@@ -782,7 +812,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
       if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
         double ct;
         int cl;
-        eval_left_deep(sc, C, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
+        eval_left_deep(sc, C, p0, p1, p2, v0, v1, v2, inv, dom, best_t, ct, cl, tie);
         if (ct < best_t) {  // strict: the earlier component wins ties (:384)
           best_t = ct;
           best_leaf = cl;

@@ -265,8 +265,14 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
       if (!(v == 0.0 || (av >= 0x1p-823 && av < 0x1p677))) tame = false;
     }
     h.flags = tame ? 1 : 0;
-    for (const prt::Comp& C : comps)
+    bool small = true;  // every root box within +-1e6: the dominant-axis quick prune's rounding stays below its margin
+    for (const prt::Comp& C : comps) {
       if (C.shape == prt::SHAPE_GENERIC) h.flags |= 2;
+      if (C.flags & 1)  // (only proven boxes are pruned)
+        for (double v : C.root_box)
+          if (!(std::fabs(v) <= 1e6)) small = false;
+    }
+    if (small) h.flags |= 4;
 
   }
   auto align8 = [](int x) { return (x + 7) & ~7; };

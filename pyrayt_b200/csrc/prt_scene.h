@@ -82,6 +82,7 @@ struct BlobHeader {
   int max_slots;   // largest component hit-list length
   int flags;       // bit 0: every bounding-box span is 0 or in [2^-823, 2^677) (fast slab test allowed)
                    // bit 1: some component has SHAPE_GENERIC (needs the interpreter kernel variant)
+                   // bit 2: every component root box lies within +-1e6 (dominant-axis quick prune allowed)
   int off_comps;   // Comp[n_components]
 };
 
