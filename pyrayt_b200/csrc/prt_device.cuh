@@ -800,6 +800,11 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
       const Comp& C = sc.comps[c];
       const int shape = C.shape;
       if (shape == SHAPE_LEAF) {  // bare TracerSurface component: no list needed
+        if (((C.flags & 4) != 0) & (dom.near >= 0)) {  // same quick prune as eval_left_deep
+          const double t_far = (C.root_box[dom.near ^ 1] - dom.o) * dom.r;
+          const double t_near = (C.root_box[dom.near] - dom.o) * dom.r;
+          if ((t_far < -2 * kCullMargin) | (t_near > best_t + 2 * kCullMargin)) continue;
+        }
         double t0, t1;
         leaf_hits(sc.leaves[C.leaf_a], p0, p1, p2, v0, v1, v2, t0, t1);
         const double t = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);

@@ -206,7 +206,22 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
       C.begin = comp_begin[c];
       C.end = (int)enc.ops.size();
       C.leaf_a = C.leaf_b = C.leaf_c = -1;
-      if (shape == prt::SHAPE_LEAF) C.leaf_a = o[0].a;
+      if (shape == prt::SHAPE_LEAF) {
+        C.leaf_a = o[0].a;
+        // a bare surface has no box in the reference; the encoder gives it one for the quick prune only:
+        // the world box of the primitive, inflated by 1e-6 of its size (hit points carry rounding of their own)
+        Box3 b;
+        if (leaf_world_box(d, C.leaf_a, b)) {
+          bool ok = true;
+          for (int k = 0; k < 3; ++k) {
+            const double pad = 1e-6 * (1.0 + std::fmax(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+            C.root_box[2 * k] = b.lo[k] - pad;
+            C.root_box[2 * k + 1] = b.hi[k] + pad;
+            if (!std::isfinite(C.root_box[2 * k]) || !std::isfinite(C.root_box[2 * k + 1])) ok = false;
+          }
+          if (ok) C.flags |= 4;  // bit 2: root_box bounds this bare leaf
+        }
+      }
       if (shape == prt::SHAPE_LEFT2) {
         C.leaf_a = o[1].a;
         C.leaf_b = o[2].b;
@@ -268,7 +283,7 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
     bool small = true;  // every root box within +-1e6: the dominant-axis quick prune's rounding stays below its margin
     for (const prt::Comp& C : comps) {
       if (C.shape == prt::SHAPE_GENERIC) h.flags |= 2;
-      if (C.flags & 1)  // (only proven boxes are pruned)
+      if (C.flags & 5)  // (only proven boxes are pruned)
         for (double v : C.root_box)
           if (!(std::fabs(v) <= 1e6)) small = false;
     }

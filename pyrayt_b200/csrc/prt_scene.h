@@ -49,6 +49,7 @@ struct Comp {
   int flags;   // bit 0: the root box provably contains the solid -> pruning allowed
                // bit 1: the solid is convex (INTERSECT of convex primitives): a ray that has just left
                //        it through one of its faces cannot hit it again before it changes direction
+               // bit 2: SHAPE_LEAF only: root_box is a conservative world box of the bare surface (quick prune)
   int begin, end;                  // ops [begin, end)
   int leaf_a, leaf_b, leaf_c;      // SHAPE_LEAF: leaf_a; SHAPE_LEFT2: a, b; SHAPE_LEFT3: a, b, c
   int op1, op2;                    // (A op1 B) op2 C
