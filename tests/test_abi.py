@@ -64,3 +64,34 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "libprt_oracle" not in text and "trace_oracle" not in text, f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/pyrayt_b200.h is the boundary a C / cgo / JNI caller binds: it must compile as C11 and the
+    library must link and answer from a C program (entry points that need no GPU)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "pyrayt_b200.h"\n'
+        "int main(void) {\n"
+        "  prt_params p; memset(&p, 0, sizeof p);\n"
+        "  if (prt_abi_version() != PRT_ABI_VERSION) return 1;\n"
+        "  if (prt_tile_rays() != 256) return 2;\n"
+        "  if (prt_axis_table_blocks(2049) != 3) return 3;\n"
+        "  /* argument validation happens before any CUDA call */\n"
+        "  if (prt_trace(NULL, &p, NULL, 0, 0, NULL, NULL, NULL) == PRT_OK) return 4;\n"
+        "  if (strlen(prt_last_error()) == 0) return 5;\n"
+        '  printf("abi %d\\n", prt_abi_version());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "use_abi"
+    libdir = os.path.join(ROOT, "pyrayt_b200")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+           "-o", str(exe), "-L", libdir, "-lpyrayt_b200", f"-Wl,-rpath,{libdir}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.strip() == f"abi {_lib.ABI_VERSION}", (run.returncode, run.stderr)
