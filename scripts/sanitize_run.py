@@ -4,8 +4,9 @@
     compute-sanitizer --tool racecheck python scripts/sanitize_run.py
     compute-sanitizer --tool synccheck python scripts/sanitize_run.py
 
-Golden cases (all record modes, staging overflow + retry), sources, component.intersect, nearest / render hits,
-the ordering kernels and the frame read-outs; every result is compared with the oracle.
+Golden cases (all record modes, staging overflow + retry, the wavefront driver, the captured small-trace
+sequence, the lean host transfer), sources, component.intersect, nearest / render hits, the ordering kernels
+and the frame read-outs; every result is compared with the oracle.
 """
 import os
 import sys
@@ -32,6 +33,16 @@ for name in GOLDEN_CASES:
     assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), name
     res = eng.trace(d, generation_limit=gl, capacity=64, to_host=True)  # overflow, then the exact retry
     assert np.array_equal(res.frame.numpy(), want, equal_nan=True), name
+    wave = eng.trace_wavefront(d, generation_limit=gl, capacity=50)  # overflow, then the exact retry
+    assert np.array_equal(wave.frame.cpu().numpy(), want, equal_nan=True), name
+    lean = eng.trace(d, generation_limit=gl, to_host=True, lean=True)  # pack kernel + host rebuild
+    assert np.array_equal(lean.frame.numpy(), want, equal_nan=True), name
+    if eng.small_fits(rays.shape[1], min(gl, 16)):
+        sub, _ = oracle.trace(scene, rays, min(gl, 16))
+        eng.small_ray_buffer(rays.shape[1]).copy_(d)
+        for _ in range(3):  # eager, captured, replayed
+            small = eng.trace_small(rays.shape[1], generation_limit=min(gl, 16))
+            assert np.array_equal(small.frame.numpy(), sub, equal_nan=True), name
     sid = int(scene.leaf_sid[-1])
     res = eng.trace(d, generation_limit=gl, record="surface", detector_sid=sid)
     assert np.array_equal(res.frame.cpu().numpy(), want[:, want[5] == sid], equal_nan=True), name
