@@ -13,8 +13,13 @@ e2e    = the same through the host-buffer API: rays in pinned host memory are co
          traced, ordered, and the whole frame is copied D2H, all inside the timed region.
 roofline / roofline_fp64 / cpu_baseline: see DESIGN.md "Measurement".
 
---impl reference times the CPU restatement of the reference (oracle/, all host threads) on a
-bounded sample of the same workload; the Python reference itself cannot travel to the GPU box.
+--scaling weak (default): every rank traces --rays rays (N x larger source); --scaling strong: the
+workload's ray count is split over the ranks by ray-index range (config 4: "16M rays at 1/2/4/8 GPUs").
+
+--impl reference times the reference's own CPU path on this box's host cores, on a bounded sample of
+the same workload: the UNMODIFIED NumPy reference (baseline/_ref, staged by oracle/stage_reference.py;
+one process per core over ray-index ranges) when it is present, with the multithreaded C restatement
+(oracle/, "port") timed beside it; the port alone otherwise.
 """
 import argparse
 import json
@@ -29,7 +34,10 @@ if ROOT not in sys.path:
 
 METRIC = "traced rays/s"
 UNIT = "rays/s"
-CPU_SAMPLE_RAYS = 1 << 18
+CPU_SAMPLE_RAYS = 1 << 18          # oracle port (C restatement), all host threads
+NUMPY_SAMPLE_RAYS_1CORE = 1 << 14  # unmodified NumPy reference as a user runs it (one core), ~10 s
+NUMPY_SAMPLE_RAYS_PER_PROC = 1 << 12  # reference arm: rays per worker process and step
+MISMATCH_SAMPLE_RAYS = 1 << 12     # stable-vs-default argsort report
 
 
 def parse_args():
@@ -39,7 +47,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config4")
-    ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
+    ap.add_argument("--rays", type=int, default=0,
+                    help="rays per GPU (weak) / in total (strong); default: the workload's")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-numpy", action="store_true", help="skip the NumPy-reference legs even if baseline/_ref exists")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--zero-copy", action="store_true", help="e2e: gather kernel writes straight into pinned host memory")
@@ -115,14 +126,27 @@ class ClockSampler:
                 "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(load)}
 
 
+def host_rays(workload, n, first=0, total=None):
+    """The workload's rays [first, first + n) as a host array (NumPy restatement of the device sources)."""
+    from oracle import sources_np
+
+    return sources_np.from_source(workload.source, n, first, total)
+
+
+def port_sample_size(workload, n):
+    """Rays the port traces per step: a ReferenceSourceSet needs a multiple of its source count."""
+    k = len(getattr(workload.source, "templates", (None,)))
+    return max(k, (min(CPU_SAMPLE_RAYS, n) // k) * k)
+
+
 def cpu_reference_run(workload, n_sample, threads, steps, warmup):
     """Times the oracle port (CPU restatement of the reference) on the first n_sample rays."""
     import numpy as np
 
-    from oracle import oracle, sources_np
+    from oracle import oracle
 
     scene = workload.scene()
-    rays = sources_np.from_source(workload.source, n_sample)
+    rays = host_rays(workload, n_sample)
     cap = n_sample * min(workload.generation_limit, 40)
     frame = np.empty((15, cap))
     times, rows, ctr = [], 0, {}
@@ -134,28 +158,95 @@ def cpu_reference_run(workload, n_sample, threads, steps, warmup):
             times.append(dt)
     mean = sum(times) / len(times)
     return {"rays_per_s": n_sample / mean, "tests_per_s": ctr["generations"] * scene.n_leaves / mean,
-            "rows": rows, "ms_per_step": mean * 1e3, "counters": ctr}
+            "rows": rows, "ms_per_step": mean * 1e3, "counters": ctr, "steps": steps, "warmup": warmup}
+
+
+def numpy_reference_available(args):
+    if getattr(args, "no_numpy", False):
+        return False
+    try:
+        from oracle import ref_shim
+
+        return ref_shim.available()
+    except Exception:
+        return False
+
+
+def numpy_reference_run(workload, n_sample, processes, steps, warmup):
+    """Times the UNMODIFIED NumPy reference (RayTracer.trace() through a FixedSource holding the same
+    seeded rays) on the first n_sample rays; processes > 1 = one process per contiguous ray range."""
+    from oracle import ref_scenes
+
+    k = len(getattr(workload.source, "templates", (None,)))
+    n_sample = max(k, (n_sample // k) * k)
+    rays = host_rays(workload, n_sample)
+    times, rows = [], 0
+    for it in range(warmup + steps):
+        r = ref_scenes.time_reference(workload.name, rays, workload.generation_limit, processes)
+        rows = r["rows"]
+        if it >= warmup:
+            times.append(r["seconds"])
+    mean = sum(times) / len(times)
+    return {"rays_per_s": n_sample / mean, "rows": rows, "ms_per_step": mean * 1e3, "rays": n_sample,
+            "processes": r["processes"], "steps": steps, "warmup": warmup}
+
+
+def argsort_mismatch_report(workload, n):
+    """SURVEY 9-Q3 / north star: rows of the reference's own frame that differ between the stable argsort
+    (the parity contract; pinned numpy 1.20 behaviour) and this numpy's default argsort."""
+    from oracle import ref_scenes
+
+    k = len(getattr(workload.source, "templates", (None,)))
+    n = max(k, (min(MISMATCH_SAMPLE_RAYS, n) // k) * k)
+    rep = ref_scenes.argsort_mismatch(workload.name, host_rays(workload, n), workload.generation_limit)
+    rep["what"] = ("unmodified reference, same seeded rays, np.argsort kind='stable' (the contract the kernel "
+                   "matches bit for bit) vs this numpy's default argsort")
+    return rep
 
 
 def run_reference(args):
-    """The reference arm: CPU implementation of the path on this box's host cores (rank 0 only)."""
+    """The reference arm: the reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from pyrayt_b200 import workloads
 
     wl = workloads.WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
-    n = min(CPU_SAMPLE_RAYS, args.rays or wl.n_rays)
-    r = cpu_reference_run(wl, n, threads, max(1, args.steps), max(0, min(args.warmup, 1)))
-    sample = f"first {n} rays of {wl.name} ({wl.description}), full frame written on the host"
+    cores = os.cpu_count() or 1
+    n_total = args.rays or wl.n_rays
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    port_n = port_sample_size(wl, n_total)
+    line_cfg = {"workload": wl.name, "description": wl.description, "generation_limit": wl.generation_limit}
+    if numpy_reference_available(args):
+        n = min(n_total, NUMPY_SAMPLE_RAYS_PER_PROC * cores)
+        r = numpy_reference_run(wl, n, cores, steps, warmup)
+        port = cpu_reference_run(wl, port_n, cores, 2, 1)
+        kind = "reference"
+        sample = (f"first {r['rays']} rays of {wl.name} ({wl.description}) through the UNMODIFIED NumPy reference "
+                  f"(pyrayt.RayTracer.trace via a FixedSource, stable argsort), {r['processes']} processes over "
+                  f"contiguous ray ranges, wall clock incl. per-process scene construction and the pandas frame")
+        extra = {"port": {"value": port["rays_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                          "sample": f"first {port_n} rays, multithreaded C restatement (oracle/), full frame written",
+                          "steps": port["steps"], "warmup": port["warmup"]}}
+        used = r["processes"]
+        tests_per_s = None
+    else:
+        r = cpu_reference_run(wl, port_n, cores, steps, warmup)
+        kind = "port"
+        sample = (f"first {port_n} rays of {wl.name} ({wl.description}), multithreaded C restatement of the "
+                  "reference (oracle/), full frame written on the host; the NumPy reference is not staged "
+                  "(baseline/_ref missing)")
+        extra = {}
+        used = cores
+        tests_per_s = r["tests_per_s"]
+        r["rays"] = port_n
+    line_cfg["rays_per_step"] = r["rays"]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["rays_per_s"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.name, "description": wl.description, "generation_limit": wl.generation_limit,
-                   "rays_per_step": n},
-        "ray_surface_tests_per_s": r["tests_per_s"],
-        "cpu_baseline": {"value": r["rays_per_s"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": line_cfg,
+        "ray_surface_tests_per_s": tests_per_s,
+        "cpu_baseline": dict({"value": r["rays_per_s"], "unit": UNIT, "cores": used, "kind": kind,
+                              "sample": sample}, **extra),
         "e2e": {"value": r["rays_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,13 +297,19 @@ def main():
     numa_node = pdist.bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
 
     wl = workloads.WORKLOADS[args.workload]
-    n = args.rays or wl.n_rays
     G = wl.generation_limit
     scene = wl.scene()
     engine = pyrayt_b200.Engine(scene, device=local_rank)
     engine.host_threads = max(2, (os.cpu_count() or 16) // world)  # ranks share the host's cores
-    first = rank * n  # ray-index range of this rank: ids stay global
-    d_rays = wl.source.generate(n, device=local_rank, first_index=first)
+    # ray-index range of this rank (ids stay global): weak = every rank brings its own --rays rays,
+    # strong = the workload's rays split over the ranks
+    n_total = (args.rays or wl.n_rays) * (world if args.scaling == "weak" else 1)
+    first, last = pdist.shard_range(n_total, rank, world)
+    n = last - first
+    if isinstance(wl.source, pyrayt_b200.sources.ReferenceSourceSet):
+        d_rays = wl.source.generate(n, device=local_rank, first_index=first, total=n_total)
+    else:
+        d_rays = wl.source.generate(n, device=local_rank, first_index=first)
     torch.cuda.synchronize()
 
     def barrier():
@@ -270,8 +367,9 @@ def main():
     counters = res.counters
     launches_per_step = res.launches
     ms_per_step = total_ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
     tests_per_s = sum_over_ranks(res.ray_surface_tests) / (ms_per_step * 1e-3)
+    rows_total = int(sum_over_ranks(rows))
     k1 = sum(k1_ms) / len(k1_ms)
 
     # ------------------------------------------------------------------ roofline of the trace kernel
@@ -293,12 +391,15 @@ def main():
         with open(traffic_file) as fh:
             t = json.load(fh)
         if t.get("workload") == wl.name and t.get("rays") == n:
+            # STORED values: one `ncu --set full` capture of this kernel on this workload made by the builder
+            # (profiles/), not counters of this run -- a bench number is never taken under a profiler
             roof["traffic"] = t.get("dram_bytes_per_launch")
-            roof["traffic_source"] = t.get("source")
-            # what the counters say the pipe actually did (pruning answers tests without executing them,
+            roof["traffic_source"] = "stored: " + str(t.get("source"))
+            # what the counters say the pipes actually did (pruning answers tests without executing them,
             # so the algorithmic fraction above can exceed it)
-            roof64["ncu_fp64_pipe_active_pct"] = t.get("fp64_pipe_active_pct")
-            roof64["ncu_issue_active_pct"] = t.get("issue_active_pct")
+            roof64["executed_work_stored_ncu"] = {
+                "fp64_pipe_active_pct": t.get("fp64_pipe_active_pct"), "issue_active_pct": t.get("issue_active_pct"),
+                "kernel_ms_under_ncu": t.get("kernel_ms"), "source": "stored: " + str(t.get("source"))}
 
     # ------------------------------------------------------------------ read-out on the device frame (N2)
     # outside the timed steps: what a user reads off the frame (per-field spot on the detector) without
@@ -306,7 +407,7 @@ def main():
     from pyrayt_b200 import analytics
 
     det = float(scene.leaf_sid[-1])
-    per_group = (world * n + 8) // 9
+    per_group = (n_total + 8) // 9
     analytics.spot_stats(res, per_group, 9, surface=det)
     r0, r1 = ev(), ev()
     r0.record()
@@ -324,37 +425,51 @@ def main():
     res = None  # drop the device frame of the last resident step before the host-buffer run
     torch.cuda.empty_cache()
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ranks)
+        e2e = run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, max_over_ranks)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1)
-    cpu = None
+    cpu, mismatch = None, None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        ns = min(CPU_SAMPLE_RAYS, n)
+        ns = port_sample_size(wl, n)
         r = cpu_reference_run(wl, ns, threads, 2, 1)
-        cpu = {"value": r["rays_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {ns} rays of {wl.name}, oracle port (C restatement), full frame written",
-               "ray_surface_tests_per_s": r["tests_per_s"]}
+        port = {"value": r["rays_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"first {ns} rays of {wl.name}, oracle port (multithreaded C restatement), full frame written",
+                "ray_surface_tests_per_s": r["tests_per_s"]}
+        if numpy_reference_available(args):
+            # the metric's own baseline: the unmodified NumPy reference as a user runs it (one process;
+            # NumPy's elementwise kernels are single-threaded), same seeded rays
+            q = numpy_reference_run(wl, min(NUMPY_SAMPLE_RAYS_1CORE, n), 1, 1, 0)
+            cpu = {"value": q["rays_per_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"first {q['rays']} rays of {wl.name} through the UNMODIFIED NumPy reference "
+                             "(pyrayt.RayTracer.trace, FixedSource with the same seeded rays, stable argsort), "
+                             "one process, wall clock of one trace() incl. the pandas frame",
+                   "rows": q["rows"], "port": port}
+            mismatch = argsort_mismatch_report(wl, n)
+        else:
+            cpu = port
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "description": wl.description, "rays_per_gpu": n,
-                       "generation_limit": G, "leaves": scene.n_leaves, "rows_per_ray": rows / n,
+            "config": {"workload": wl.name, "description": wl.description, "rays_per_gpu": n, "rays_total": n_total,
+                       "generation_limit": G, "leaves": scene.n_leaves, "rows_per_ray": rows / max(n, 1),
                        "parallelism": f"ray-range x{world}", "numa_node_rank0": numa_node, "l2": "inputs larger than L2 (rays + staging >> 126 MB)"},
-            "ray_surface_tests_per_s": tests_per_s, "segments_per_s": world * rows / (ms_per_step * 1e-3),
+            "ray_surface_tests_per_s": tests_per_s, "segments_per_s": rows_total / (ms_per_step * 1e-3),
             "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e, "readout": readout,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "counters": {k: counters[k] for k in ("rays", "generations", "segments", "tie_rays", "rows_dropped")},
+            "argsort_mismatch": mismatch,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ranks):
+def run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, max_over_ranks):
     """Host buffers in, host frame out: H2D of the rays and D2H of the frame inside the timed region."""
     import psutil
 
@@ -389,7 +504,7 @@ def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ra
     ms = max_over_ranks(t0.elapsed_time(t1)) / steps
     chk = float(h_frame[5, :1024].sum())  # touch the host result
     lean = engine.last_transfer == "lean"  # what the timed steps used (chosen by the engine's own timing)
-    out = {"value": world * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+    out = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
            "h2d_bytes_per_step": int(h_rays.numel() * 8),
            "d2h_bytes_per_step": int(rows * 11 * 8 + 8) if lean else int(frame_bytes),
            "host_frame_bytes_per_step": int(frame_bytes),
@@ -408,7 +523,7 @@ def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ra
     from pyrayt_b200 import analytics
 
     det = float(engine.scene.leaf_sid[-1])
-    per_group = (world * n + 8) // 9
+    per_group = (n_total + 8) // 9
 
     def step_readout():
         dev_in.copy_(h_rays, non_blocking=True)
@@ -427,7 +542,7 @@ def run_e2e(args, torch, engine, d_rays, n, G, rows, world, barrier, max_over_ra
     out["with_device_readout"] = {
         "what": "host rays in -> trace -> analytics.spot_stats on the device frame -> 9 x 17 table out "
                 "(the frame is not copied)",
-        "value": world * n / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
+        "value": n_total / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
         "d2h_bytes_per_step": int(table.shape[0] * table.shape[1] * 8)}
     return out
 

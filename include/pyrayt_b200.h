@@ -237,7 +237,9 @@ int prt_gather_frame(const prt_records* records, int32_t generation_limit, const
  * input values) and surface (a small integer).  prt_frame_pack writes one word per row,
  * (index of the ray in d_rays) << 24 | (surface id + 1), after checking row by row that the frame holds
  * exactly what the host will rebuild (ids consecutive from d_rays' first id, intensity / wavelength
- * bit-equal to the ray's, surface id an integer in [-1, 2^24 - 2]); *d_bad receives the number of rows
+ * bit-equal to the ray's, surface id an integer in [-1, 2^24 - 2], generation = the ray's own value in the
+ * rows before d_gen_offsets[1] and g in [d_gen_offsets[g], d_gen_offsets[g+1]); d_gen_offsets holds
+ * generation_limit + 1 entries as written by prt_scan_runs); *d_bad receives the number of rows
  * that failed -- if it is not zero the caller must copy all fifteen columns instead.
  * prt_host_expand_frame (host code, `threads` worker threads) then fills columns 0, 1, 2, 4, 5 of a host
  * frame from the packed words, the per-generation row offsets and host copies of rows 8, 9, 10 and 12 of the RaySet
@@ -245,7 +247,8 @@ int prt_gather_frame(const prt_records* records, int32_t generation_limit, const
  * other ten columns are copied as usual: 88 instead of 120 bytes per row cross the bus.
  */
 int prt_frame_pack(const double* d_frame, int64_t rows, int64_t frame_stride, const double* d_rays, int64_t n_rays,
-                   int64_t ray_stride, uint64_t* d_packed, uint64_t* d_bad, void* cuda_stream);
+                   int64_t ray_stride, const int64_t* d_gen_offsets, int32_t generation_limit, uint64_t* d_packed,
+                   uint64_t* d_bad, void* cuda_stream);
 int prt_host_expand_frame(const uint64_t* h_packed, int64_t rows, const int64_t* h_gen_offsets,
                           int32_t generation_limit, const double* h_ray_generation, const double* h_ray_intensity,
                           const double* h_ray_wavelength, const double* h_ray_id, double* h_frame,
@@ -295,8 +298,10 @@ typedef struct prt_source_desc {
                           the reference's deterministic sources (pyrayt/components.py:511-613):
                           10 = LineOfRays, 11 = CircleOfRays, 12 = ConeOfRays, 13 = WedgeOfRays with
                           p[0] = spacing | diameter | cone angle [rad] | wedge angle [rad], p[1] = wavelength,
-                          p[2] = ray count of the source (== n_rays), p[3] = id of its first ray,
-                          p[4..15] = rows 0..2 of the source's 4x4 world matrix (first_index unused)      */
+                          p[2] = ray count of the source, p[3] = id of its first ray,
+                          p[4..15] = rows 0..2 of the source's 4x4 world matrix; a call writes the window
+                          [first_index, first_index + n_rays) of the source's p[2] rays (a rank's share of
+                          a sharded source; first_index = 0, n_rays = p[2] for the whole source)         */
   int32_t reserved;
   uint64_t seed;
   double origin[3];
@@ -343,8 +348,10 @@ int prt_spot_centers(const double* d_sums, const double* d_center_in, int32_t n_
 
 /*
  * The focus table of cells 12 and 15: one column per selected row, in frame order, rows
- * {id, radius, focus, wavelength}: radius = y0 of the ray's generation-0 row (the first gen0_rows
- * rows of the frame, ids first_id .. first_id + gen0_rows - 1 in order; NaN if absent),
+ * {id, radius, focus, wavelength}: radius = y0 of the ray's generation-0 row, found by bisection on
+ * the id column of the first gen0_rows rows (generation-0 rows are in id order; rays that miss in
+ * generation 0 have no row, so ids there need not be consecutive; first_id, the lowest ray id, only
+ * seeds the search; NaN if the ray has no generation-0 row),
  * focus = -x_tilt*y0/y_tilt + x0.  Row k of output column j at d_table[k*table_stride + j]; at most
  * table_capacity columns are written.  Workspace: d_block_count / d_block_base hold
  * prt_axis_table_blocks(rows) entries; d_total[1] receives the number of selected rows (d_total[0] = 0).

@@ -1,11 +1,15 @@
-"""Import the UNMODIFIED PyRayT reference (pure Python) from /root/reference.
+"""Import the UNMODIFIED PyRayT reference (pure Python).
 
-TEST INFRASTRUCTURE ONLY.  This module is used in the build container to
-(1) validate the C restatement in ``oracle/trace_oracle.c`` against the real
-reference and (2) generate the golden fixtures committed under
-``tests/golden/``.  ``/root/reference`` does not exist on the GPU box, so
-nothing on the product path, in ``bench.py`` or in the ``-m gpu`` tests may
-import this file.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Used (1) to validate the C restatement in
+``oracle/trace_oracle.c`` against the real reference, (2) to generate the golden fixtures
+committed under ``tests/golden/``, (3) by ``bench.py``'s NumPy arm (``cpu_baseline.kind =
+"reference"``) and (4) by the ``gpu`` + ``reference`` drop-in tests.  Nothing under
+``pyrayt_b200/`` imports this file.
+
+Search order: ``$PYRAYT_REF``, ``/root/reference`` (build container), ``baseline/_ref`` (the
+git-ignored install made by ``oracle/stage_reference.py``; it travels with the repo snapshot, so
+it is what the GPU box sees -- ``/root/reference`` does not exist there and is never read at run
+time by the ``-m gpu`` tests, ``smoke()`` or ``bench.py``).
 
 Two shims are applied *outside* the read-only reference tree:
 
@@ -26,11 +30,27 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PYRAYT_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("PYRAYT_REF"), "/root/reference", STAGED):
+        if cand and os.path.isdir(os.path.join(cand, "pyrayt")) and os.path.isdir(os.path.join(cand, "tinygfx")):
+            return cand
+    return os.environ.get("PYRAYT_REF", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "pyrayt"))
+
+
+def examples_dir() -> str:
+    """The reference's examples/ directory (scripts the drop-in tests run unchanged)."""
+    return os.path.join(REF_ROOT, "examples")
 
 
 def load():

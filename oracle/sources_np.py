@@ -82,8 +82,15 @@ def generate(kind: int, seed: int, origin, p, n: int, first_index: int = 0) -> n
     return rays
 
 
-def from_source(src, n: int, first_index: int = 0) -> np.ndarray:
-    """Same rays as ``pyrayt_b200.sources.SyntheticSource.generate`` (host array)."""
+def from_source(src, n: int, first_index: int = 0, total=None) -> np.ndarray:
+    """Same rays as ``pyrayt_b200.sources.SyntheticSource.generate`` /
+    ``ReferenceSourceSet.generate`` (host array)."""
+    if hasattr(src, "windows"):  # ReferenceSourceSet: concatenated reference sources, ids renumbered
+        out = np.empty((13, n))
+        for s, first, count, off in src.windows(n, first_index, total):
+            full = reference_source(s.kind, list(s.p), int(s.p[2]))
+            out[:, off:off + count] = full[:, first:first + count]
+        return out
     return generate(src.kind, src.seed, tuple(src.origin), list(src.p), n, first_index)
 
 

@@ -142,7 +142,7 @@ def load():
     lib.prt_axis_table.restype = ctypes.c_int
     lib.prt_axis_table.argtypes = [vp, i64, i64, i32, f64, i64, i64, vp, vp, vp, vp, i64, i64, vp]
     lib.prt_frame_pack.restype = ctypes.c_int
-    lib.prt_frame_pack.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp, vp]
+    lib.prt_frame_pack.argtypes = [vp, i64, i64, vp, i64, i64, vp, i32, vp, vp, vp]
     lib.prt_host_expand_frame.restype = ctypes.c_int
     lib.prt_host_expand_frame.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, i64, i32]
     lib.prt_fp64_probe.restype = ctypes.c_int

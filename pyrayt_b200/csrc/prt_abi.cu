@@ -40,8 +40,8 @@ cudaError_t prt_launch_axis_table(const double* frame, long long rows, long long
                                   long long* total, double* table, long long table_stride, long long table_capacity,
                                   cudaStream_t st);
 cudaError_t prt_launch_frame_pack(const double* frame, long long rows, long long stride, const double* rays,
-                                  long long n_rays, long long ray_stride, unsigned long long* packed,
-                                  unsigned long long* bad, cudaStream_t st);
+                                  long long n_rays, long long ray_stride, const long long* gen_off, int generations,
+                                  unsigned long long* packed, unsigned long long* bad, cudaStream_t st);
 void prt_host_expand_rows(const uint64_t* packed, int64_t r0, int64_t r1, const int64_t* gen_off, int32_t generations,
                           const double* r_gen, const double* r_int, const double* r_wl, const double* r_id,
                           double* frame, int64_t frame_stride);
@@ -317,7 +317,8 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
   const bool synthetic = src->kind >= 1 && src->kind <= 3;
   const bool reference = src->kind >= 10 && src->kind <= 13;
   if (!synthetic && !reference) return fail(PRT_ERR_INVALID, "unknown source kind");
-  if (reference && (double)n_rays != src->p[2]) return fail(PRT_ERR_INVALID, "n_rays must equal the source's ray count p[2]");
+  if (reference && (first_index < 0 || (double)(first_index + n_rays) > src->p[2]))
+    return fail(PRT_ERR_INVALID, "window [first_index, first_index + n_rays) exceeds the source's ray count p[2]");
   if (ray_stride < n_rays) return fail(PRT_ERR_INVALID, "ray_stride < n_rays");
   cudaError_t e = prt_launch_source(src, d_rays, n_rays, ray_stride, first_index, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "source kernel launch");
@@ -325,11 +326,14 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
 }
 
 int prt_frame_pack(const double* d_frame, int64_t rows, int64_t frame_stride, const double* d_rays, int64_t n_rays,
-                   int64_t ray_stride, uint64_t* d_packed, uint64_t* d_bad, void* cuda_stream) {
+                   int64_t ray_stride, const int64_t* d_gen_offsets, int32_t generation_limit, uint64_t* d_packed,
+                   uint64_t* d_bad, void* cuda_stream) {
   if (rows < 0 || (rows > 0 && (!d_frame || !d_packed)) || frame_stride < rows) return fail(PRT_ERR_INVALID, "bad frame");
   if (!d_bad) return fail(PRT_ERR_INVALID, "d_bad is NULL");
   if (rows > 0 && (n_rays < 1 || !d_rays || ray_stride < n_rays)) return fail(PRT_ERR_INVALID, "bad ray buffer");
+  if (rows > 0 && (!d_gen_offsets || generation_limit < 1)) return fail(PRT_ERR_INVALID, "generation offsets missing");
   cudaError_t e = prt_launch_frame_pack(d_frame, rows, frame_stride, d_rays, n_rays, ray_stride,
+                                        reinterpret_cast<const long long*>(d_gen_offsets), generation_limit,
                                         reinterpret_cast<unsigned long long*>(d_packed),
                                         reinterpret_cast<unsigned long long*>(d_bad), (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "frame pack launch");

@@ -303,11 +303,24 @@ __global__ void __launch_bounds__(256) axis_table_kernel(const double* __restric
     const long long r = base + u * 256;
     const double id = frame[kColId * stride + r];
     // results.loc[(generation == 0) & id.isin(...)]['y0']: generation-0 rows are the first rows of the
-    // frame, one per ray, in id order
-    const long long r0 = (long long)id - first_id;
+    // frame in id order, but not one per ray -- a ray that misses everything in generation 0 has no row --
+    // so the row is found by bisection on the id column (first_id only seeds the search: row id - first_id
+    // when no earlier ray missed)
     double radius = NAN;
-    if (r0 >= 0 && r0 < gen0_rows && frame[kColId * stride + r0] == id && frame[kColGeneration * stride + r0] == 0.0)
-      radius = frame[kColY0 * stride + r0];
+    {
+      const double* ids = frame + kColId * stride;
+      long long lo = 0, hi = gen0_rows;  // first row in [0, gen0_rows) with ids[row] >= id
+      const long long guess = (long long)id - first_id;
+      if (guess >= 0 && guess < gen0_rows && ids[guess] == id) {
+        lo = hi = guess;
+      }
+      while (lo < hi) {
+        const long long mid = lo + ((hi - lo) >> 1);
+        if (ids[mid] < id) lo = mid + 1; else hi = mid;
+      }
+      if (lo < gen0_rows && ids[lo] == id && frame[kColGeneration * stride + lo] == 0.0)
+        radius = frame[kColY0 * stride + lo];
+    }
     table[0 * table_stride + dst] = id;
     table[1 * table_stride + dst] = radius;
     table[2 * table_stride + dst] = axis_focus(frame, stride, r);

@@ -481,11 +481,14 @@ __global__ void source_kernel(const prt_source_desc src, double* rays, long long
 // normalisation (:481-496).  p[0] = spacing | diameter | cone angle [rad] | wedge angle [rad],
 // p[1] = wavelength, p[2] = rays of this source, p[3] = id of its first ray, p[4..15] = rows 0..2
 // of the source's world matrix.  linspace / arange arithmetic follows NumPy's formulas exactly;
-// sin/cos are the CUDA double-precision functions (within 1-2 ulp of NumPy's).
-__global__ void reference_source_kernel(const prt_source_desc src, double* rays, long long stride) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// sin/cos are the CUDA double-precision functions (within 1-2 ulp of NumPy's).  A launch writes the
+// window [first, first + count) of the source's n rays (a rank's share of a sharded source).
+__global__ void reference_source_kernel(const prt_source_desc src, double* rays, long long stride, long long first,
+                                        long long count) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)src.p[2];
-  if (j >= n) return;
+  if (w >= count) return;
+  const long long j = first + w;
   const double jd = (double)j, nd = (double)n;
   double lx = 0, ly = 0, lz = 0, ux = 0, uy = 0, uz = 0;
   const double two_pi = 2 * 3.141592653589793;
@@ -535,7 +538,7 @@ __global__ void reference_source_kernel(const prt_source_desc src, double* rays,
   dx /= nrm;
   dy /= nrm;
   dz /= nrm;
-  double* r = rays + j;
+  double* r = rays + w;
   r[0 * stride] = px;
   r[1 * stride] = py;
   r[2 * stride] = pz;
@@ -661,7 +664,7 @@ cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long lon
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (src->kind >= 10)
-    prt::reference_source_kernel<<<blocks, 256, 0, st>>>(*src, rays, stride);
+    prt::reference_source_kernel<<<blocks, 256, 0, st>>>(*src, rays, stride, first, n);
   else
     prt::source_kernel<<<blocks, 256, 0, st>>>(*src, rays, n, stride, first);
   return cudaGetLastError();

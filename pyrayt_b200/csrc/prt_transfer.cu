@@ -4,8 +4,8 @@
 // carry no information of their own: `generation` follows from the row's position, `intensity`,
 // `wavelength` and `id` are copies of the ray's input values, `surface` is a small integer.  The pack
 // kernel folds them into one 64-bit word per row -- (index of the ray in the input RaySet) << 24 |
-// (surface id + 1) -- after *verifying* row by row that the frame's values are exactly the ones the
-// host will reconstruct; the host then fills those five columns from its own copy of the rays while
+// (surface id + 1) -- after *verifying* row by row that the frame's values (all five columns, the
+// generation included) are exactly the ones the host will reconstruct; the host then fills those five columns from its own copy of the rays while
 // the other ten columns are still streaming over the bus (88 instead of 120 B per row on PCIe).
 // Any row that does not verify (ids that are not consecutive, surface ids outside 24 bits, NaN
 // metadata) makes the caller fall back to copying all fifteen columns.
@@ -27,6 +27,7 @@ namespace prt {
 __global__ void __launch_bounds__(256) frame_pack_kernel(const double* __restrict__ frame, long long rows,
                                                          long long stride, const double* __restrict__ rays,
                                                          long long n_rays, long long ray_stride,
+                                                         const long long* __restrict__ gen_off, int generations,
                                                          unsigned long long* __restrict__ packed,
                                                          unsigned long long* __restrict__ bad) {
   const double id0 = rays[12 * ray_stride];
@@ -40,8 +41,16 @@ __global__ void __launch_bounds__(256) frame_pack_kernel(const double* __restric
     // (the host rebuilds id as id0 + index: both directions of that identity are checked)
     bool ok = idx >= 0 && idx < n_rays && (double)idx == rel && id0 + (double)idx == id && s >= -1 && (double)s == sid;
     if (ok) {
+      // generation of row r = the last g with gen_off[g] <= r (the host walks the same offsets); the column
+      // must hold the ray's own generation value in generation 0 and g afterwards (pyrayt/_pyrayt.py:440-441)
+      int lo = 0, hi = generations;  // gen_off[0] = 0 <= r < gen_off[generations] = rows
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (gen_off[mid] <= r) lo = mid; else hi = mid;
+      }
+      const double want_gen = (lo == 0) ? rays[8 * ray_stride + idx] : (double)lo;
       ok = rays[12 * ray_stride + idx] == id && rays[9 * ray_stride + idx] == frame[1 * stride + r] &&
-           rays[10 * ray_stride + idx] == frame[2 * stride + r];
+           rays[10 * ray_stride + idx] == frame[2 * stride + r] && frame[0 * stride + r] == want_gen;
     }
     packed[r] = ok ? (((unsigned long long)idx << 24) | (unsigned long long)(s + 1)) : ~0ull;
     my_bad += ok ? 0u : 1u;
@@ -67,13 +76,14 @@ static inline void store_stream(double* p, double v) {
 extern "C" {
 
 cudaError_t prt_launch_frame_pack(const double* frame, long long rows, long long stride, const double* rays,
-                                  long long n_rays, long long ray_stride, unsigned long long* packed,
-                                  unsigned long long* bad, cudaStream_t st) {
+                                  long long n_rays, long long ray_stride, const long long* gen_off, int generations,
+                                  unsigned long long* packed, unsigned long long* bad, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess || rows == 0) return e;
   const long long want = (rows + 255) / 256;
   const unsigned grid = (unsigned)std::min<long long>(want, 148LL * 32);
-  prt::frame_pack_kernel<<<grid, 256, 0, st>>>(frame, rows, stride, rays, n_rays, ray_stride, packed, bad);
+  prt::frame_pack_kernel<<<grid, 256, 0, st>>>(frame, rows, stride, rays, n_rays, ray_stride, gen_off, generations,
+                                               packed, bad);
   return cudaGetLastError();
 }
 

@@ -407,9 +407,11 @@ class Engine:
                 out[c, :rows].copy_(frame[c, :rows], non_blocking=True)
             stream.synchronize()
         else:
+            d_goff = self._buf("pack_goff", len(goff), torch.int64)
+            d_goff[: len(goff)].copy_(torch.from_numpy(np.ascontiguousarray(goff, dtype=np.int64)), non_blocking=True)
             _lib.check(self.lib.prt_frame_pack(frame.data_ptr(), rows, int(frame.stride(0)), d_rays.data_ptr(), n,
-                                               int(d_rays.stride(0)), packed.data_ptr(), bad.data_ptr(),
-                                               self._stream()), "prt_frame_pack")
+                                               int(d_rays.stride(0)), d_goff.data_ptr(), len(goff) - 1,
+                                               packed.data_ptr(), bad.data_ptr(), self._stream()), "prt_frame_pack")
             h_packed[:rows].copy_(packed, non_blocking=True)
             h_bad.copy_(bad, non_blocking=True)
             if host_rays is None:

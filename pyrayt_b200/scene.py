@@ -68,15 +68,29 @@ def _material_record(material) -> tuple:
     if not hasattr(material, "trace"):
         # e.g. the Gooch BLACK cylinder inside components.aperture()
         return MAT_UNTRACEABLE, [0.0] * 6
-    names = {k.__name__ for k in type(material).__mro__}
-    if "_AbsorbingMaterial" in names:
-        return MAT_ABSORBER, [0.0] * 6
-    if "_ReflectingMaterial" in names:
-        return MAT_MIRROR, [0.0] * 6
-    if "SellmeierRefractor" in names:
-        return MAT_GLASS_SELLMEIER, [float(getattr(material, k)) for k in ("b1", "b2", "b3", "c1", "c2", "c3")]
-    if "BasicRefractor" in names:
-        return MAT_GLASS_CONST, [float(material._refractive_index)] + [0.0] * 5
+    # The kernel implements exactly four laws.  A material is recognised by the reference class it derives
+    # from, and only if nothing between its own class and that base re-defines trace() / index_at() (a
+    # partial mirror, a custom dispersion law, ...): such a material cannot run on the device and there is
+    # no CPU fallback, so it is an error rather than being silently traced as its base class.
+    known = {"_AbsorbingMaterial": MAT_ABSORBER, "_ReflectingMaterial": MAT_MIRROR,
+             "SellmeierRefractor": MAT_GLASS_SELLMEIER, "BasicRefractor": MAT_GLASS_CONST}
+    mro = type(material).__mro__
+    base = next((k for k in mro if k.__name__ in known), None)
+    if base is not None:
+        overriding = [k.__name__ for k in mro[: mro.index(base)] if "trace" in vars(k) or "index_at" in vars(k)]
+        if any(name in getattr(material, "__dict__", {}) for name in ("trace", "index_at")):
+            overriding.append("the instance itself")
+        if overriding:
+            raise SceneError(
+                f"material {type(material).__name__} overrides trace()/index_at() of {base.__name__} "
+                f"(in {', '.join(overriding)}); only the reference's own absorber, mirror, BasicRefractor and "
+                "SellmeierRefractor laws run on the B200 path (no CPU fallback)")
+        kind = known[base.__name__]
+        if kind == MAT_GLASS_SELLMEIER:
+            return kind, [float(getattr(material, k)) for k in ("b1", "b2", "b3", "c1", "c2", "c3")]
+        if kind == MAT_GLASS_CONST:
+            return kind, [float(material._refractive_index)] + [0.0] * 5
+        return kind, [0.0] * 6
     raise SceneError(
         f"material {type(material).__name__} has a custom trace()/index_at(); only absorber, mirror, "
         "BasicRefractor and SellmeierRefractor run on the B200 path (no CPU fallback)"
@@ -255,7 +269,13 @@ def flatten(components: Iterable) -> FlatScene:
         leaf_mat.append(kind)
         leaf_matp.append(matp)
 
+    seen = set()
     for comp in components:
+        # the same component object listed twice: the reference intersects it twice and the second copy can
+        # never win _st_propagate's strict `<` (pyrayt/_pyrayt.py:384), so it is dropped here
+        if id(comp) in seen:
+            continue
+        seen.add(id(comp))
         emit(comp)
         comp_begin.append(len(node_kind))
 

@@ -31,26 +31,9 @@ import pyrayt.materials as matl  # noqa: E402
 import tinygfx.g3d as cg  # noqa: E402
 
 
-class FixedSource(pc.Source):
-    """Feeds a fixed (13,N) array through the reference's Source interface."""
+from oracle import ref_scenes  # noqa: E402  (scene builders + the reference's trace() on a fixed RaySet)
 
-    def __init__(self, rays):
-        super().__init__()
-        self._fixed = np.array(rays, dtype=np.float64)
-
-    def _local_ray_generation(self, n):
-        rs = pyrayt.RaySet(self._fixed.shape[1])
-        rs[:] = self._fixed
-        return rs
-
-
-def reference_trace(rays, components, generation_limit):
-    tracer = pyrayt.RayTracer(FixedSource(rays), components)
-    tracer.set_rays_per_source(rays.shape[1])
-    tracer.set_generation_limit(generation_limit)
-    with ref_shim.stable_argsort(), np.errstate(all="ignore"):
-        df = tracer.trace()
-    return df.to_numpy(dtype=np.float64).T.copy() if len(df) else np.zeros((15, 0))
+reference_trace = ref_scenes.reference_trace
 
 
 def cone(n, half_deg, apex, seed, wavelength=0.633):
@@ -68,11 +51,7 @@ def config1_collimator():
     return [lens, baffle], np.array(src.generate_rays(50)), 100
 
 
-def config2_scene():
-    lens = pc.biconvex_lens(2, 2, 0.25, aperture=1)
-    stop = pc.aperture((1, 1), 0.6).move_x(0.5)
-    det = pc.baffle((1, 1)).move_x(1)
-    return [lens, stop, det]
+config2_scene = ref_scenes.config2_scene
 
 
 def config2_tutorial():
@@ -80,10 +59,7 @@ def config2_tutorial():
     return config2_scene(), sources_np.from_source(workloads.CONFIG2_SOURCE, 4096), 100
 
 
-def config3_scene():
-    prism = pc.equilateral_prism(1, 1).move_x(0.25)
-    baffle = pc.baffle((1, 1)).rotate_y(90).move(1, 0, -0.5)
-    return [prism, baffle]
+config3_scene = ref_scenes.config3_scene
 
 
 def config3_rays(per_source):
@@ -98,19 +74,7 @@ def config3_prism():
     return config3_scene(), config3_rays(96), 10
 
 
-def config4_scene():
-    """10-element spherical-lens stack with two stops and a detector."""
-    comps = []
-    for i in range(10):
-        if i % 2 == 0:
-            lens = pc.thick_lens(60, -60, 4, aperture=25.4, material=matl.glass["BK7"])
-        else:
-            lens = pc.thick_lens(-80, 80, 2, aperture=25.4, material=matl.glass["SF5" if i % 4 == 1 else "SF2"])
-        comps.append(lens.move_x(10 * i))
-    comps.append(pc.aperture((25.4, 25.4), 12.0).move_x(35))
-    comps.append(pc.aperture((25.4, 25.4), 12.0).move_x(75))
-    comps.append(pc.baffle((25.4, 25.4)).move_x(100))
-    return comps
+config4_scene = ref_scenes.config4_scene
 
 
 CONFIG4_SOURCE = workloads.CONFIG4_SOURCE
@@ -120,25 +84,7 @@ def config4_stack():
     return config4_scene(), sources_np.from_source(CONFIG4_SOURCE, 1536), 64
 
 
-def config5_scene():
-    """Multi-bounce paraboloid / TIR light-pipe / cuboid-mirror scene.
-
-    A point source at the focus of ``parabolic_mirror(50, 5, aperture=40)`` (focus at the origin)
-    emits towards -x; the dish returns a collimated beam along +x.  ``m1`` (cuboid mirror, tilted
-    0.3 deg) sends it back to the dish, which focuses it through the origin into the end face of a
-    BK7 ``Cuboid.from_sides(200, 10, 10)`` light pipe whose axis is tilted 20 deg to the beam: rays
-    zig-zag down the pipe by total internal reflection (about 9 glass interactions per ray), leave
-    through the far face, and a second cuboid mirror ``m2`` folds them onto the detector baffle.
-    Part of the outgoing beam also crosses the pipe sideways (two refractions).  Measured with the
-    reference: 12.4 rows per ray on average, 51 % of the rays end on the detector.
-    """
-    c20, s20 = np.cos(np.radians(20.0)), np.sin(np.radians(20.0))
-    parab = pc.parabolic_mirror(50, 5, aperture=40)
-    pipe = cg.Cuboid.from_sides(200, 10, 10, material=matl.glass["BK7"]).rotate_z(20).move(106 * c20, 106 * s20, 0)
-    m1 = pc.plane_mirror(2, aperture=(60, 60)).rotate_z(0.3).move(120, 0, 0)
-    m2 = pc.plane_mirror(2, aperture=(60, 60)).rotate_z(-35).move(241 * c20, 241 * s20, 0)
-    det = pc.baffle((80, 80)).rotate_z(90).move(226, 160, 0)
-    return [parab, pipe, m1, m2, det]
+config5_scene = ref_scenes.config5_scene
 
 
 CONFIG5_SOURCE = workloads.CONFIG5_SOURCE

@@ -138,6 +138,39 @@ def test_spot_stats_and_focus_table_match_oracle(name, cuda_device):
 
 
 @pytest.mark.gpu
+def test_focus_table_when_rays_miss_in_generation_zero(cuda_device):
+    """Rays that hit nothing in generation 0 have no row, so the head of the frame is compacted and a
+    later ray's generation-0 row is not at (id - first_id): the radius must still be its own y0
+    (the notebook's results.loc[(generation == 0) & id.isin(...)]['y0'])."""
+    import torch
+
+    import pyrayt_b200
+    from oracle import analytics_np
+    from pyrayt_b200 import analytics
+
+    scene, rays, _, gl = load_case("config1_collimator")
+    rays = np.tile(rays, (1, 8))
+    n = rays.shape[1]
+    rays[12] = 1000 + np.arange(n)  # ids need not start at 0 either
+    miss = (np.arange(n) % 3 == 0) | (np.arange(n) < 7)
+    rays[4, miss] *= -1.0  # pointing away from the lens: no hit, no row
+    eng = pyrayt_b200.Engine(scene, device=0)
+    res = eng.trace(torch.from_numpy(np.ascontiguousarray(rays)).cuda(), generation_limit=gl)
+    frame = res.frame.cpu().numpy()
+    assert 0 < int(res.gen_counts[0]) == n - int(miss.sum())
+    results = _df(frame)
+    sid, gmax = _last_surface(frame)
+    for sel in (dict(surface=sid), dict(generation=gmax), dict(generation=0.0), dict()):
+        want = analytics_np.focus_table(results, **sel)
+        for first_id in (1000, 0):  # the hint may be right, or useless
+            got = analytics.focus_table(res, first_id=first_id, **sel)
+            assert len(got) == len(want) > 0
+            assert not np.any(np.isnan(np.asarray(got["radius"])))
+            for col in ("id", "radius", "focus", "wavelength"):
+                assert np.array_equal(np.asarray(got[col]), np.asarray(want[col]), equal_nan=True), (sel, col)
+
+
+@pytest.mark.gpu
 def test_analytics_edge_cases(cuda_device):
     import torch
 

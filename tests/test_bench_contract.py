@@ -10,9 +10,10 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
 
 
-def test_reference_arm_prints_one_contract_line():
+def _reference_arm(*extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rays", "4096",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--steps", "1", "--warmup", "1", *extra], capture_output=True, text=True, timeout=600,
+                         cwd=ROOT)
     assert out.returncode == 0, out.stderr[-500:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -21,8 +22,29 @@ def test_reference_arm_prints_one_contract_line():
     assert d["metric"] == "traced rays/s" and d["unit"] == "rays/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["gpu_launches"] == 0 and d["dtype"] == "f64"
     assert d["config"]["workload"] == "config4"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert (d["steps"], d["warmup"]) == (1, 1)  # what actually ran
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"] and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    return d
+
+
+def test_reference_arm_port_only():
+    """Without the staged NumPy reference the arm times the C restatement and says so."""
+    d = _reference_arm("--no-numpy")
+    assert d["cpu_baseline"]["kind"] == "port"
+
+
+def test_reference_arm_times_the_numpy_reference_when_staged():
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        import pytest
+
+        pytest.skip("PyRayT reference not present")
+    d = _reference_arm()
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and "UNMODIFIED NumPy reference" in cb["sample"]
+    assert cb["port"]["kind"] == "port" and cb["port"]["value"] > cb["value"]  # the port is the harder baseline
 
 
 def test_other_ranks_of_the_reference_arm_stay_silent():

@@ -61,11 +61,44 @@ def test_unsupported_things_are_hard_errors():
     with pytest.raises(sc.SceneError):
         sc.flatten([object()])
     s = fakes.Surface(fakes.Sphere(1), fakes._AbsorbingMaterial())
-    with pytest.raises(sc.SceneError):
-        sc.flatten([s, s])  # the same surface twice
+    with pytest.raises(sc.SceneError):  # the same surface inside two different components
+        sc.flatten([fakes.CSG(s, fakes.Surface(fakes.Sphere(1), fakes._AbsorbingMaterial()), 2, (-1, 1) * 3),
+                    fakes.CSG(s, fakes.Surface(fakes.Sphere(2), fakes._AbsorbingMaterial()), 2, (-1, 1) * 3)])
     too_many = [fakes.Surface(fakes.Sphere(1), fakes._AbsorbingMaterial()) for _ in range(sc.MAX_LEAVES + 1)]
     with pytest.raises(sc.SceneError):
         sc.flatten(too_many)
+
+
+def test_repeated_component_is_listed_once():
+    """The reference accepts the same component twice; the copy can never win the strict `<`."""
+    s = fakes.Surface(fakes.Sphere(1), fakes._AbsorbingMaterial())
+    t = fakes.Surface(fakes.Sphere(2), fakes._AbsorbingMaterial())
+    flat = sc.flatten([s, t, s])
+    assert flat.n_components == 2 and list(flat.leaf_sid) == [s.get_id(), t.get_id()]
+
+
+def test_material_subclasses_that_override_the_law_are_rejected():
+    """A subclass of a reference material that re-defines trace() / index_at() must not be traced as its base."""
+    class HalfMirror(fakes._ReflectingMaterial):
+        def trace(self, surface, ray_set):
+            return ray_set
+
+    class Cauchy(fakes.BasicRefractor):
+        def index_at(self, wavelength):
+            return 1.5 + 0.004 / wavelength ** 2
+
+    class Renamed(fakes.SellmeierRefractor):  # no override: still the reference's law
+        pass
+
+    for bad in (HalfMirror(), Cauchy(1.5)):
+        with pytest.raises(sc.SceneError, match="overrides"):
+            sc.flatten([fakes.Surface(fakes.Sphere(1), bad)])
+    patched = fakes._AbsorbingMaterial()
+    patched.trace = lambda surface, ray_set: ray_set  # instance-level override
+    with pytest.raises(sc.SceneError, match="overrides"):
+        sc.flatten([fakes.Surface(fakes.Sphere(1), patched)])
+    flat = sc.flatten([fakes.Surface(fakes.Sphere(1), Renamed(1.0, 0.2, 1.0, 0.006, 0.02, 103.0))])
+    assert flat.leaf_mat[0] == sc.MAT_GLASS_SELLMEIER
 
 
 def test_untraceable_material_is_flagged_not_rejected():

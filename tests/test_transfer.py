@@ -72,3 +72,25 @@ def test_lean_transfer_equals_full_copy(cuda_device):
     want, _ = oracle.trace(scene, shifted, gl)
     got = eng.trace(torch.from_numpy(shifted).cuda(), generation_limit=gl, to_host=True, lean=True)
     assert np.array_equal(got.frame.numpy(), want, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_lean_transfer_verifies_the_generation_column(cuda_device):
+    """A device frame whose generation column is not what the host would rebuild from the row offsets
+    (caller-edited here) must be copied in full, not silently 'corrected'."""
+    import torch
+
+    import pyrayt_b200
+
+    scene, rays, _, gl = load_case("config4_stack")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    d = torch.from_numpy(np.ascontiguousarray(rays)).cuda()
+    res = eng.trace(d, generation_limit=gl)
+    goff = np.concatenate(([0], np.cumsum(res.gen_counts)))
+    ok = eng._frame_to_host(res.frame, res.rows, goff, d, lean=True).numpy().copy()
+    assert eng.last_transfer == "lean" and np.array_equal(ok, res.frame.cpu().numpy(), equal_nan=True)
+    edited = res.frame.clone()
+    edited[0, res.rows // 2] = 77.0
+    got = eng._frame_to_host(edited, res.rows, goff, d, lean=True).numpy()
+    assert eng.last_transfer == "full"
+    assert np.array_equal(got, edited.cpu().numpy(), equal_nan=True)
