@@ -66,6 +66,23 @@ def main():
         return ""
 
     print(f"total warp-instructions {tot}, stall samples {tots}")
+    if os.environ.get("HOT_RANGES"):
+        # HOT_RANGES="file:lo-hi=name,..." : executed instructions / samples per named line range
+        groups = {}
+        spec = []
+        for part in os.environ["HOT_RANGES"].split(","):
+            loc, name = part.split("=")
+            f, rng = loc.split(":")
+            lo, hi = rng.split("-")
+            spec.append((f, int(lo), int(hi), name))
+        for (f, ln), (e, t, sm) in agg.items():
+            name = next((n for (ff, lo, hi, n) in spec if ff == f and lo <= ln <= hi), f"other:{f}")
+            g = groups.setdefault(name, [0, 0])
+            g[0] += e
+            g[1] += sm
+        for name, (e, sm) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
+            print(f"{100 * e / tot:5.1f}% inst {100 * sm / max(tots, 1):5.1f}% smp  {name}")
+        return
     for (f, ln), (e, t, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         print(f"{100 * e / tot:5.1f}% inst {100 * s / max(tots, 1):5.1f}% smp  {f}:{ln:<4d} {src(f, ln)[:100]}")
 
