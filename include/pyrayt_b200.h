@@ -48,13 +48,14 @@
 extern "C" {
 #endif
 
-#define PRT_ABI_VERSION 1
+#define PRT_ABI_VERSION 2
 
 /* rows of the reference RaySet, (13, N) float64 row-major (pyrayt/_pyrayt.py:13-144) */
 #define PRT_RAY_ROWS 13
 /* columns of the results frame (pyrayt/_pyrayt.py:15,:154-165):
  * generation,intensity,wavelength,index,id,surface,x0,y0,z0,x1,y1,z1,x_tilt,y_tilt,z_tilt */
 #define PRT_FRAME_COLS 15
+#define PRT_STAGE_COLS 9  /* doubles per staged record, see prt_records */
 /* hit slots one component may produce = 2 x leaves of the component */
 #define PRT_MAX_SLOTS 32
 /* largest scene the kernel stages in shared memory */
@@ -154,7 +155,10 @@ typedef struct prt_counters {
  * column-major staging buffer and notes (start, count) in the run table.
  */
 typedef struct prt_records {
-  double* d_stage;      /* [PRT_FRAME_COLS * capacity] staging, column c row r at d_stage[c*capacity + r] */
+  double* d_stage;      /* [PRT_STAGE_COLS * capacity] staged records, column c row r at d_stage[c*capacity + r]:
+                           start position (3), direction as traced (3), hit distance, refractive index before the
+                           interaction, (slot of the ray in its tile) << 32 | leaf hit -- what only the trace knows
+                           about a row; prt_gather_frame expands it into the 15 frame columns               */
   int64_t capacity;     /* rows                                                                           */
   int64_t* d_run_start; /* [generation_limit * n_tiles], index g*n_tiles + tile                           */
   int32_t* d_run_count; /* [generation_limit * n_tiles]                                                   */
@@ -223,13 +227,20 @@ int prt_scan_runs(const prt_records* records, int32_t generation_limit, int64_t*
                   void* cuda_stream);
 
 /*
- * Copy staged rows to the final frame in (generation, id) order.
+ * Expand the staged records into the final frame in (generation, id) order: the row
+ * _RayTraceDataframe.insert builds (pyrayt/_pyrayt.py:168-186) -- generation / intensity / wavelength / id
+ * from the RaySet the trace was given (same d_rays, n_rays, ray_stride), surface id from the scene, end
+ * point = start + direction * distance, unit tilt -- computed with the trace kernel's own functions, so the
+ * frame is bit-identical to writing the columns in the trace.
  * layout 0: column-major, column c row r at frame[c*frame_stride + r]  (what pandas holds)
  * layout 1: row-major,    row r column c at frame[r*PRT_FRAME_COLS + c]
+ * Rows at or beyond frame_capacity are not written (the caller sizes the frame from a hint, reads
+ * d_gen_offsets[generation_limit] afterwards and repeats with a larger frame if it was short).
  * `frame` may be any device-accessible pointer, including pinned host memory.
  */
-int prt_gather_frame(const prt_records* records, int32_t generation_limit, const int64_t* d_gen_offsets,
-                     double* frame, int64_t frame_stride, int32_t layout, void* cuda_stream);
+int prt_gather_frame(prt_scene* scene, const prt_records* records, const double* d_rays, int64_t n_rays,
+                     int64_t ray_stride, int32_t generation_limit, const int64_t* d_gen_offsets, double* frame,
+                     int64_t frame_stride, int64_t frame_capacity, int32_t layout, void* cuda_stream);
 
 /*
  * Lean device -> host transfer of a frame.  Five of the fifteen columns can be rebuilt on the host from

@@ -12,8 +12,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYRAYT_B200_LIB") or os.path.join(_HERE, "libpyrayt_b200.so")  # override: experiments only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FRAME_COLS = 15
+STAGE_COLS = 9  # doubles per staged record (PRT_STAGE_COLS)
 RAY_ROWS = 13
 RECORD_ALL, RECORD_SURFACE, RECORD_NONE = 0, 1, 2
 SELECT_ALL, SELECT_SURFACE, SELECT_GENERATION = 0, 1, 2
@@ -121,7 +122,7 @@ def load():
     lib.prt_scan_runs.restype = ctypes.c_int
     lib.prt_scan_runs.argtypes = [ctypes.POINTER(PrtRecords), i32, vp, vp]
     lib.prt_gather_frame.restype = ctypes.c_int
-    lib.prt_gather_frame.argtypes = [ctypes.POINTER(PrtRecords), i32, vp, vp, i64, i32, vp]
+    lib.prt_gather_frame.argtypes = [vp, ctypes.POINTER(PrtRecords), vp, i64, i64, i32, vp, vp, i64, i64, i32, vp]
     lib.prt_intersect.restype = ctypes.c_int
     lib.prt_intersect.argtypes = [vp, i32, vp, i64, vp, vp, ctypes.POINTER(i32), vp]
     lib.prt_generate_source.restype = ctypes.c_int

@@ -19,10 +19,7 @@ extern "C" {
 cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, cudaStream_t st);
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
                             long long* gen_offsets, cudaStream_t st);
-cudaError_t prt_launch_gather(const double* stage, long long capacity, const long long* run_start,
-                              const int* run_count, const long long* run_base, long long n_tiles,
-                              const long long* gen_offsets, int generation_limit, double* frame,
-                              long long frame_stride, int layout, cudaStream_t st);
+cudaError_t prt_launch_gather(const prt::GatherArgs* a, int layout, cudaStream_t st);
 cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int component, const double* rays,
                                  long long n, double* hits, long long* sids, int slots, cudaStream_t st);
 cudaError_t prt_launch_source(const prt_source_desc* src, double* rays, long long n, long long stride,
@@ -258,17 +255,36 @@ int prt_scan_runs(const prt_records* rec, int32_t generation_limit, int64_t* d_g
   return PRT_OK;
 }
 
-int prt_gather_frame(const prt_records* rec, int32_t generation_limit, const int64_t* d_gen_offsets, double* frame,
-                     int64_t frame_stride, int32_t layout, void* cuda_stream) {
+int prt_gather_frame(prt_scene* scene, const prt_records* rec, const double* d_rays, int64_t n_rays,
+                     int64_t ray_stride, int32_t generation_limit, const int64_t* d_gen_offsets, double* frame,
+                     int64_t frame_stride, int64_t frame_capacity, int32_t layout, void* cuda_stream) {
+  if (!scene) return fail(PRT_ERR_INVALID, "null scene");
   if (!rec || !rec->d_stage || !rec->d_run_start || !rec->d_run_count || !rec->d_run_base || !d_gen_offsets)
     return fail(PRT_ERR_INVALID, "null argument");
   if (!frame) return fail(PRT_ERR_INVALID, "null frame");
+  if (n_rays < 0 || (n_rays > 0 && !d_rays) || ray_stride < n_rays) return fail(PRT_ERR_INVALID, "bad ray buffer");
   if (layout != 0 && layout != 1) return fail(PRT_ERR_INVALID, "bad layout");
+  if (frame_capacity < 0 || (layout == 0 && frame_stride < frame_capacity)) return fail(PRT_ERR_INVALID, "bad frame");
   if (rec->n_tiles > 0x7fffffffLL) return fail(PRT_ERR_LIMIT, "too many tiles");
-  cudaError_t e = prt_launch_gather(rec->d_stage, rec->capacity, reinterpret_cast<long long*>(rec->d_run_start),
-                                    rec->d_run_count, reinterpret_cast<long long*>(rec->d_run_base), rec->n_tiles,
-                                    reinterpret_cast<const long long*>(d_gen_offsets), generation_limit, frame,
-                                    frame_stride, layout, (cudaStream_t)cuda_stream);
+  if (rec->n_tiles * (int64_t)prt::kTileRays < n_rays) return fail(PRT_ERR_INVALID, "records.n_tiles too small");
+  prt::GatherArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.blob = scene->d_blob;
+  a.rays = d_rays;
+  a.n_rays = n_rays;
+  a.ray_stride = ray_stride;
+  a.stage = rec->d_stage;
+  a.capacity = rec->capacity;
+  a.run_start = reinterpret_cast<const long long*>(rec->d_run_start);
+  a.run_count = rec->d_run_count;
+  a.run_base = reinterpret_cast<const long long*>(rec->d_run_base);
+  a.n_tiles = rec->n_tiles;  // the run tables are indexed g * n_tiles + tile; tiles without rays have empty runs
+  a.gen_offsets = reinterpret_cast<const long long*>(d_gen_offsets);
+  a.generation_limit = generation_limit;
+  a.frame = frame;
+  a.frame_stride = frame_stride;
+  a.frame_capacity = frame_capacity;
+  cudaError_t e = prt_launch_gather(&a, layout, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "gather kernel launch");
   return PRT_OK;
 }

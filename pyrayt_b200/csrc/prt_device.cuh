@@ -142,6 +142,9 @@ struct SceneView {
   const Op* ops;
   const double* aabb;
   const Leaf* leaves;
+  const OrderEntry* order;   // [6][n_boxed] traversal tables
+  const OrderEntry* bycomp;  // [6][n_components] the same entries in list order
+  const int* unboxed;        // [n_unboxed]
 };
 
 PRT_HD SceneView make_view(const unsigned char* blob) {
@@ -151,6 +154,9 @@ PRT_HD SceneView make_view(const unsigned char* blob) {
   s.ops = reinterpret_cast<const Op*>(blob + s.h->off_ops);
   s.aabb = reinterpret_cast<const double*>(blob + s.h->off_aabb);
   s.leaves = reinterpret_cast<const Leaf*>(blob + s.h->off_leaves);
+  s.order = reinterpret_cast<const OrderEntry*>(blob + s.h->off_order);
+  s.unboxed = reinterpret_cast<const int*>(blob + s.h->off_unboxed);
+  s.bycomp = reinterpret_cast<const OrderEntry*>(blob + s.h->off_bycomp);
   return s;
 }
 
@@ -656,41 +662,38 @@ PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
   cl = take ? leaf : cl;
 }
 
-// The ray's dominant axis, for a two-instruction version of the proven-box pruning: along one axis the
-// far face of a box gives an upper bound of the exit distance b1 and the near face a lower bound of the
-// entry distance b0, so "far < -margin" or "near > best + margin" (with twice the margin, which swallows
-// the rounding of the unguarded product) implies the exact test below would prune as well.
+// The ray's dominant axis, for the ordered traversal of the boxed components (nearest_hit).  Along one
+// axis the far face of a box bounds its exit distance from above and the near face its entry distance from
+// below, so with u = +-x_k (sign chosen so that the ray runs towards +u), uo the origin and a = |d_k|:
+//   far_u  < uo - 3 m a          =>  the box ends at least 3 m behind the ray: no positive hit possible
+//   near_u > uo + (best + 2 m) a =>  the box begins more than 2 m - rounding beyond the best hit so far
+// (m = kCullMargin; |u| <= 1e6 and 1/4 <= a <= 4 keep the rounding of both right-hand sides below 1e-9,
+// far inside the margins; hit parameters and box parameters of the same point differ by ~1e-13).  Both
+// imply that the exact proven-box test of the component would prune it as well.
 struct DomAxis {
-  double o, r;  // origin coordinate and reciprocal direction along the axis
-  int near;     // index of the near face in a 6-span box (the far face is near ^ 1); < 0: quick test not usable
+  double thr_far, a;  // uo - 3 m a (boxes ending before it are behind the ray), |direction component|
+  int table;          // 2 * axis + sign: which traversal table; < 0: quick tests not usable for this ray
 };
 
-PRT_HD DomAxis make_dom_axis(double p0, double p1, double p2, double v0, double v1, double v2, const RayInv& inv,
-                             bool small_boxes) {
+PRT_HD DomAxis make_dom_axis(double p0, double p1, double p2, double v0, double v1, double v2, bool small_boxes) {
   const double a0 = fabs(v0), a1 = fabs(v1), a2 = fabs(v2);
   const int k = (a0 >= a1) ? ((a0 >= a2) ? 0 : 2) : ((a1 >= a2) ? 1 : 2);
-  const double a = (k == 0) ? a0 : ((k == 1) ? a1 : a2);
   DomAxis d;
-  d.o = (k == 0) ? p0 : ((k == 1) ? p1 : p2);
-  d.r = (k == 0) ? inv.r0 : ((k == 1) ? inv.r1 : inv.r2);
-  const int s = (inv.bits >> (3 + k)) & 1;
-  // with |o|, |face| <= 1e6 and 1/4 <= |d| <= 4 the product below is off by < 1e-8, well inside the doubled margin
-  d.near = (small_boxes && fabs(d.o) <= 1e6 && a >= 0.25 && a <= 4.0) ? 2 * k + s : -1;
+  d.a = (k == 0) ? a0 : ((k == 1) ? a1 : a2);
+  const double o = (k == 0) ? p0 : ((k == 1) ? p1 : p2);
+  const double v = (k == 0) ? v0 : ((k == 1) ? v1 : v2);
+  const int s = v < 0 ? 1 : 0;
+  d.thr_far = (s ? -o : o) - (3 * kCullMargin) * d.a;
+  d.table = (small_boxes && fabs(o) <= 1e6 && d.a >= 0.25 && d.a <= 4.0) ? 2 * k + s : -1;
   return d;
 }
 
 // shapes 2/3: (A op1 B) [op2 C] with their bounding boxes (csg.py:118-160 for a left-deep tree)
 PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double p1, double p2, double v0, double v1,
-                           double v2, const RayInv& inv, const DomAxis& dom, double best_t, double& ct, int& cl,
-                           bool& tie) {
+                           double v2, const RayInv& inv, double best_t, double& ct, int& cl, bool& tie) {
   ct = PRT_INF;
   cl = -1;
   const int shape = C.shape;
-  if (((C.flags & 1) != 0) & (dom.near >= 0)) {
-    const double t_far = (C.root_box[dom.near ^ 1] - dom.o) * dom.r;
-    const double t_near = (C.root_box[dom.near] - dom.o) * dom.r;
-    if ((t_far < -2 * kCullMargin) | (t_near > best_t + 2 * kCullMargin)) return;
-  }
   double b0, b1;
   cube_hits(C.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
   if (!(b0 < PRT_INF)) return;  // csg.py:126-133
@@ -782,8 +785,14 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
   take_hit(kc1, c1, lc, ct, cl);
 }
 
-// nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386); components are
-// visited in order (the earlier one wins ties)
+// nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386).  The reference visits the
+// components in list order and replaces the running best only by a strictly smaller distance (:384), i.e.
+// the smallest distance wins and, among equal distances, the earliest component.  Stated that way the result
+// does not depend on the visiting order, so the boxed components are visited in the order the ray meets
+// their boxes (see OrderEntry / DomAxis): the entries behind the ray are skipped by bisection, and the walk
+// stops at the first box that begins beyond the best hit found so far -- in a lens train that is one or two
+// evaluated components per generation instead of a test of every component.  Components without a usable
+// box are always evaluated; rays the quick tests cannot serve visit every component in list order.
 // GENERIC = false compiles the interpreter for arbitrary trees out: scenes whose components are all
 // bare leaves or left-deep (every reference factory) run a smaller kernel with no lists in memory.
 template <bool GENERIC>
@@ -792,54 +801,79 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
   best_t = PRT_INF;
   best_leaf = -1;
   const RayInv inv = make_ray_inv(p0, p1, p2, v0, v1, v2, (sc.h->flags & 1) != 0);
-  const DomAxis dom = make_dom_axis(p0, p1, p2, v0, v1, v2, inv, (sc.h->flags & 4) != 0);
-  const int nc = sc.h->n_components;
-  {
-    for (int c = 0; c < nc; ++c) {
-      if (c == skip) continue;  // convex solid the ray left in the previous generation
-      const Comp& C = sc.comps[c];
-      const int shape = C.shape;
-      if (shape == SHAPE_LEAF) {  // bare TracerSurface component: no list needed
-        if (((C.flags & 4) != 0) & (dom.near >= 0)) {  // same quick prune as eval_left_deep
-          const double t_far = (C.root_box[dom.near ^ 1] - dom.o) * dom.r;
-          const double t_near = (C.root_box[dom.near] - dom.o) * dom.r;
-          if ((t_far < -2 * kCullMargin) | (t_near > best_t + 2 * kCullMargin)) continue;
-        }
-        double t0, t1;
-        leaf_hits(sc.leaves[C.leaf_a], p0, p1, p2, v0, v1, v2, t0, t1);
-        const double t = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
-        if (t < best_t) {
-          best_t = t;
-          best_leaf = C.leaf_a;
-        }
-        continue;
+  const DomAxis dom = make_dom_axis(p0, p1, p2, v0, v1, v2, (sc.h->flags & 4) != 0);
+  const bool quick = dom.table >= 0;                      // the threshold tests are usable for this ray
+  const bool ordered = quick & ((sc.h->flags & 8) != 0);  // walk the boxes in ray order (scenes with many components)
+  // phase 0 walks a table: the ray-ordered one from the bisection point, or the list-order one from its start
+  // (every lane of the warp then sees component c in iteration c); phase 1: the components without a box
+  const int n0 = ordered ? sc.h->n_boxed : sc.h->n_components;
+  const int n1 = ordered ? sc.h->n_unboxed : 0;
+  const OrderEntry* tab = (ordered ? sc.order : sc.bycomp) + (quick ? dom.table : 0) * n0;
+  const double thr_far = quick ? dom.thr_far : -PRT_INF;
+  double thr_near = PRT_INF;
+  int j = 0;
+  if (ordered) {
+    int hi = n0;  // first entry whose running-maximum far face is not provably behind the ray
+    while (j < hi) {
+      const int mid = (j + hi) >> 1;
+      if (tab[mid].pmfar_u < thr_far) j = mid + 1; else hi = mid;
+    }
+  }
+  int phase = (j < n0) ? 0 : 1;
+  if (phase) j = 0;
+  for (;;) {
+    int c;
+    if (phase == 0) {
+      const OrderEntry e = tab[j];
+      const bool beyond = e.near_u > thr_near;
+      const bool stop = ordered & beyond;  // ray order: every later box begins even further away
+      ++j;
+      if (stop | (j >= n0)) {
+        phase = 1;
+        j = 0;
       }
-      if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
-        double ct;
-        int cl;
-        eval_left_deep(sc, C, p0, p1, p2, v0, v1, v2, inv, dom, best_t, ct, cl, tie);
-        if (ct < best_t) {  // strict: the earlier component wins ties (:384)
-          best_t = ct;
-          best_leaf = cl;
-        }
-        continue;
-      }
-      if (GENERIC) {
-        S->flags = 0;
-        if (!eval_component(sc, C.begin, C.end, p0, p1, p2, v0, v1, v2, inv, true, best_t, *S, tie)) continue;
+      if (beyond | (e.far_u < thr_far)) continue;
+      c = e.comp;
+    } else {
+      if (j >= n1) break;
+      c = sc.unboxed[j];
+      ++j;
+    }
+    if (c == skip) continue;  // convex solid the ray left in the previous generation
+    const Comp& C = sc.comps[c];
+    const int shape = C.shape;
+    double ct = PRT_INF;
+    int cl = -1;
+    if (shape == SHAPE_LEAF) {  // bare TracerSurface component: no list needed
+      double t0, t1;
+      leaf_hits(sc.leaves[C.leaf_a], p0, p1, p2, v0, v1, v2, t0, t1);
+      ct = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
+      cl = C.leaf_a;
+    } else if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
+      eval_left_deep(sc, C, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
+    } else if (GENERIC) {
+      S->flags = 0;
+      if (eval_component(sc, C.begin, C.end, p0, p1, p2, v0, v1, v2, inv, true, best_t, *S, tie)) {
         const int b = buf_of(*S, 0);
         const int n = S->len[0];
-        for (int j = 0; j < n; ++j) {  // sorted: the first positive entry is the argmin of where(hits>0)
-          const double t = S->t[b][j];
+        for (int q = 0; q < n; ++q) {  // sorted: the first positive entry is the argmin of where(hits>0)
+          const double t = S->t[b][q];
           if (t > 0) {
-            if (t < best_t) {
-              best_t = t;
-              best_leaf = S->leaf[b][j];
-            }
+            ct = t;
+            cl = S->leaf[b][q];
             break;
           }
         }
       }
+    }
+    // smallest distance, then earliest component (== the reference's in-order strict `<`)
+    bool better = ct < best_t;
+    if ((ct == best_t) & (ct < PRT_INF)) better = c < sc.leaves[best_leaf].comp;  // rare: coincident surfaces
+    if (better) {
+      best_t = ct;
+      best_leaf = cl;
+      // uo + (ct + 2 m) a, written from thr_far = uo - 3 m a (the re-association moves it by < 1e-9)
+      if (quick) thr_near = thr_far + (ct + 5 * kCullMargin) * dom.a;
     }
   }
 }
@@ -856,7 +890,7 @@ struct StepOut {
   bool row;                  // a frame row was produced this generation
   double sid;                // surface id
   double e0, e1, e2;         // hit point (x1,y1,z1)
-  double t0n, t1n, t2n;      // unit tilt of the incoming direction
+  double t0n, t1n, t2n;      // unit tilt of the incoming direction (TILT = false: only set for glass hits)
   double nv0, nv1, nv2;      // direction after the interaction
   double n_next;             // refractive index after the interaction
   int skip;                  // component that cannot be hit in the next generation, or -1
@@ -891,7 +925,18 @@ PRT_HD double step_speed(const RayState& r, StepCounters& c) {
   return vn;
 }
 
-// second half: _st_interact for a ray whose nearest hit is (best_t, best_leaf >= 0); `vn` = step_speed
+// the row's tilt columns: the unit incoming direction (pyrayt/_pyrayt.py:177); `vn` = |v| = step_speed.
+// One definition, used by the interaction (refract()'s normalised vector is the same quotient,
+// operations.py:125) and by the ordering pass that rebuilds the columns from the staged direction.
+PRT_HD void unit_tilt(double v0, double v1, double v2, double vn, double& t0, double& t1, double& t2) {
+  const Rcp rvn = make_rcp(vn);
+  div_by3(v0, v1, v2, rvn, t0, t1, t2);
+}
+
+// second half: _st_interact for a ray whose nearest hit is (best_t, best_leaf >= 0); `vn` = step_speed.
+// TILT = false leaves o.t0n..t2n unset unless the material needs them (the trace kernel stages the
+// direction itself and the ordering pass calls unit_tilt).
+template <bool TILT = true>
 PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int generation_limit, double vn,
                           double best_t, int best_leaf, StepOut& o, StepCounters& c) {
   o.row = false;
@@ -901,9 +946,8 @@ PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int gen
   o.e2 = r.p2 + r.v2 * best_t;
   o.n_next = r.nidx;
   o.skip = -1;
-  // unit incoming direction: the row's tilt (:177) and refract()'s normalised vector (operations.py:125)
-  const Rcp rvn = make_rcp(vn);
-  div_by3(r.v0, r.v1, r.v2, rvn, o.t0n, o.t1n, o.t2n);
+  const bool is_glass = (L.mat == PRT_MAT_GLASS_CONST) | (L.mat == PRT_MAT_GLASS_SELLMEIER);
+  if (TILT || is_glass) unit_tilt(r.v0, r.v1, r.v2, vn, o.t0n, o.t1n, o.t2n);
   bool goes_on = true;
   // mirrors and glasses need the surface normal (one call site: the primitive switch is large)
   double n0 = 0, n1 = 0, n2 = 0;
@@ -990,7 +1034,7 @@ PRT_HD bool trace_step(const SceneView& sc, const RayState& r, int g, int genera
   nearest_hit<GENERIC>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, r.skip, S, best_t, best_leaf, tie);
   if (tie) c.w1 |= kCtrTie;
   if (best_leaf < 0) return false;  // miss: dead, nothing recorded (:415-420)
-  return step_interact(sc, r, g, generation_limit, vn, best_t, best_leaf, o, c);
+  return step_interact<true>(sc, r, g, generation_limit, vn, best_t, best_leaf, o, c);
 }
 
 // storage for the generic interpreter's hit lists: only the GENERIC kernel variants carry it

@@ -1,6 +1,7 @@
 // Host-side scene encoder: caller's postfix CSG programs (prt_scene_desc) -> the blob the
 // kernels stage in shared memory (prt_scene.h).  Shared by the ABI layer and tests/emul.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -222,6 +223,8 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
           if (ok) C.flags |= 4;  // bit 2: root_box bounds this bare leaf
         }
       }
+      if (shape == prt::SHAPE_GENERIC && o[0].kind == prt::OP_ENTER)  // the traversal tables need the root box
+        for (int k = 0; k < 6; ++k) C.root_box[k] = enc.aabb[6 * o[0].a + k];
       if (shape == prt::SHAPE_LEFT2) {
         C.leaf_a = o[1].a;
         C.leaf_b = o[2].b;
@@ -300,6 +303,19 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   off = align8(off + (int)sizeof(double) * 6 * h.n_aabb);
   h.off_leaves = off;
   off = align8(off + (int)sizeof(prt::Leaf) * d->n_leaves);
+  // traversal tables (see OrderEntry): only meaningful when the quick prune is allowed at all (flags bit 2)
+  std::vector<int> boxed, unboxed;
+  for (int c = 0; c < d->n_components; ++c) (((comps[c].flags & 5) && (h.flags & 4)) ? boxed : unboxed).push_back(c);
+  h.n_boxed = (int)boxed.size();
+  h.n_unboxed = (int)unboxed.size();
+  off = (off + 15) & ~15;
+  h.off_order = off;
+  off += (int)sizeof(prt::OrderEntry) * 6 * h.n_boxed;
+  h.off_unboxed = off;
+  off = (off + (int)sizeof(int) * h.n_unboxed + 15) & ~15;
+  h.off_bycomp = off;
+  off += (int)sizeof(prt::OrderEntry) * 6 * (d->n_components > 0 ? d->n_components : 1);
+  if (h.n_boxed > prt::kOrderedMinBoxed) h.flags |= 8;
   h.total_bytes = off;
   blob.assign((size_t)off, 0);
   std::memcpy(blob.data(), &h, sizeof h);
@@ -323,6 +339,41 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   for (int c = 0; c < d->n_components; ++c)
     for (int nd = d->comp_node_begin[c]; nd < d->comp_node_begin[c + 1]; ++nd)
       if (d->node_kind[nd] == PRT_LEAF) leaves[d->node_leaf[nd]].comp = c;
+
+  prt::OrderEntry* order = reinterpret_cast<prt::OrderEntry*>(blob.data() + h.off_order);
+  for (int k = 0; k < 3; ++k)
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      prt::OrderEntry* tab = order + (size_t)(2 * k + sgn) * h.n_boxed;
+      for (int j = 0; j < h.n_boxed; ++j) {
+        const prt::Comp& C = comps[boxed[j]];
+        tab[j].near_u = sgn ? -C.root_box[2 * k + 1] : C.root_box[2 * k];
+        tab[j].far_u = sgn ? -C.root_box[2 * k] : C.root_box[2 * k + 1];
+        tab[j].comp = boxed[j];
+        tab[j].pad = 0;
+      }
+      // ties in near_u keep component order (any order is correct: nearest_hit breaks ties by index)
+      std::stable_sort(tab, tab + h.n_boxed,
+                       [](const prt::OrderEntry& a, const prt::OrderEntry& b) { return a.near_u < b.near_u; });
+      double run = -INFINITY;
+      for (int j = 0; j < h.n_boxed; ++j) {
+        run = tab[j].far_u > run ? tab[j].far_u : run;
+        tab[j].pmfar_u = run;
+      }
+    }
+  if (h.n_unboxed) std::memcpy(blob.data() + h.off_unboxed, unboxed.data(), sizeof(int) * unboxed.size());
+  prt::OrderEntry* bycomp = reinterpret_cast<prt::OrderEntry*>(blob.data() + h.off_bycomp);
+  for (int t = 0; t < 6; ++t)
+    for (int c = 0; c < d->n_components; ++c) {
+      prt::OrderEntry& e = bycomp[(size_t)t * d->n_components + c];
+      const prt::Comp& C = comps[c];
+      const bool has_box = (C.flags & 5) && (h.flags & 4);
+      const int k = t >> 1, sgn = t & 1;
+      e.near_u = has_box ? (sgn ? -C.root_box[2 * k + 1] : C.root_box[2 * k]) : -INFINITY;
+      e.far_u = has_box ? (sgn ? -C.root_box[2 * k] : C.root_box[2 * k + 1]) : INFINITY;
+      e.pmfar_u = INFINITY;
+      e.comp = c;
+      e.pad = 0;
+    }
   return PRT_OK;
 }
 

@@ -42,8 +42,11 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   extern __shared__ __align__(16) unsigned char s_blob[];
   __shared__ int s_wcount[kTileRays / 32];
   __shared__ long long s_base;
-  // per-ray values only needed when a row is written live in shared memory, not in registers
-  __shared__ double s_gen0[kTileRays], s_inten[kTileRays], s_id[kTileRays];
+  // per-ray values that the nearest-hit search does not need live in shared memory, not in registers:
+  // the wavelength / refractive index (interaction only) and the event counters.  (generation, intensity
+  // and id are only ever copied into rows: the ordering pass reads them from the RaySet itself.)
+  __shared__ double s_wl[kTileRays], s_nidx[kTileRays];
+  __shared__ unsigned s_ctr0[kTileRays], s_ctr1[kTileRays];
 
   // stage the scene in shared memory once per block
   {
@@ -62,8 +65,9 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   const int warp = threadIdx.x >> 5;
 
   RayState rs = {0, 0, 0, 0, 0, 0, 0, 1, -1};
-  StepCounters sc_ctr = {0, 0};
   unsigned c_drop = 0, c_badw = 0;
+  s_ctr0[threadIdx.x] = 0;
+  s_ctr1[threadIdx.x] = 0;
   if (valid) {
     const double* r = a.rays + i;
     rs.p0 = r[0 * a.stride];
@@ -74,11 +78,8 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
     rs.v1 = r[5 * a.stride];
     rs.v2 = r[6 * a.stride];
     const double vw = r[7 * a.stride];
-    s_gen0[threadIdx.x] = r[8 * a.stride];
-    s_inten[threadIdx.x] = r[9 * a.stride];
-    rs.wl = r[10 * a.stride];
-    rs.nidx = r[11 * a.stride];
-    s_id[threadIdx.x] = r[12 * a.stride];
+    s_wl[threadIdx.x] = r[10 * a.stride];
+    s_nidx[threadIdx.x] = r[11 * a.stride];
     if (pw != 1.0 || vw != 0.0) c_badw = 1;
   }
   bool alive = valid;
@@ -87,20 +88,36 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   HitStack* S = StackFor<GENERIC>::ptr(stack_storage);
 
   for (int g = 0; g < a.generation_limit; ++g) {
-    StepOut so;
-    bool write = false;
-    bool next_alive = false;
+    // _st_propagate: nearest hit of every live ray
+    double vn = 0.0, hit_t = 0.0;
+    int hit_leaf = -1;
     if (alive) {
-      next_alive = trace_step<GENERIC>(sc, rs, g, a.generation_limit, S, so, sc_ctr);
-      alive = so.row;
-      write = RECORD && so.row && (a.record_mode == PRT_RECORD_ALL || so.sid == a.detector_sid);
+      StepCounters ctr = {s_ctr0[threadIdx.x], s_ctr1[threadIdx.x]};
+      vn = step_speed(rs, ctr);
+      if (vn != 0.0) {
+        bool tie = false;
+        nearest_hit<GENERIC>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, rs.skip, S, hit_t, hit_leaf, tie);
+        if (tie) ctr.w1 |= kCtrTie;
+      }
+      s_ctr0[threadIdx.x] = ctr.w0;
+      s_ctr1[threadIdx.x] = ctr.w1;
     }
+    // What the interaction will decide is already known from the leaf that was hit: a row is produced unless
+    // the material cannot be traced, and the ray goes on unless it is absorbed or at the generation limit
+    // (step_interact's return value, restated).  So the row -- which holds pre-interaction state only, see
+    // kStageCols -- is reserved and written first, and the interaction then updates the ray in place.
+    const int mat = (hit_leaf >= 0) ? sc.leaves[hit_leaf].mat : PRT_MAT_UNTRACEABLE;
+    const bool has_row = (hit_leaf >= 0) & (mat != PRT_MAT_UNTRACEABLE);
+    const bool next_alive = has_row & (mat != PRT_MAT_ABSORBER) & (g + 1 != a.generation_limit);
 
+    int any_alive = 1;
     if (RECORD) {
+      const bool write =
+          has_row && (a.record_mode == PRT_RECORD_ALL || sc.leaves[hit_leaf].sid == a.detector_sid);
       // block-aggregated append: one reservation per tile and generation, rows in ray order
       const unsigned m = __ballot_sync(0xffffffffu, write);
       if (lane == 0) s_wcount[warp] = __popc(m);
-      const int any_alive = __syncthreads_or(next_alive);
+      any_alive = __syncthreads_or(next_alive);
       int before = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < kTileRays / 32; ++w) {
@@ -121,39 +138,45 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
         const long long run = s_base;
         if (run + total <= a.capacity) {
           const long long row = run + before + __popc(m & ((1u << lane) - 1u));
+          // the staged record (kStageCols): pre-interaction state + what was hit; gather_kernel expands it
           double* o = a.stage + row;
           const long long cs = a.capacity;
-          o[0 * cs] = (g == 0) ? s_gen0[threadIdx.x] : (double)g;  // :440-441
-          o[1 * cs] = s_inten[threadIdx.x];
-          o[2 * cs] = rs.wl;
-          o[3 * cs] = rs.nidx;
-          o[4 * cs] = s_id[threadIdx.x];
-          o[5 * cs] = so.sid;
-          o[6 * cs] = rs.p0;
-          o[7 * cs] = rs.p1;
-          o[8 * cs] = rs.p2;
-          o[9 * cs] = so.e0;
-          o[10 * cs] = so.e1;
-          o[11 * cs] = so.e2;
-          o[12 * cs] = so.t0n;
-          o[13 * cs] = so.t1n;
-          o[14 * cs] = so.t2n;
+          o[0 * cs] = rs.p0;
+          o[1 * cs] = rs.p1;
+          o[2 * cs] = rs.p2;
+          o[3 * cs] = rs.v0;
+          o[4 * cs] = rs.v1;
+          o[5 * cs] = rs.v2;
+          o[6 * cs] = hit_t;
+          o[7 * cs] = s_nidx[threadIdx.x];
+          o[8 * cs] = __longlong_as_double(((long long)threadIdx.x << 32) | (long long)hit_leaf);
         } else {
           c_drop++;
         }
       }
-      if (!any_alive) break;
     }
 
-    alive = next_alive;
-    if (alive) {
-      advance_ray(rs, so, g, a.ray_offset);
-    } else if (!RECORD) {
-      break;
+    // _st_interact: material, new direction, offset start of the next generation
+    alive = false;
+    if (hit_leaf >= 0) {
+      StepCounters ctr = {s_ctr0[threadIdx.x], s_ctr1[threadIdx.x]};
+      StepOut so;
+      rs.wl = s_wl[threadIdx.x];
+      rs.nidx = s_nidx[threadIdx.x];
+      alive = step_interact<false>(sc, rs, g, a.generation_limit, vn, hit_t, hit_leaf, so, ctr);
+      s_ctr0[threadIdx.x] = ctr.w0;
+      s_ctr1[threadIdx.x] = ctr.w1;
+      if (alive) {
+        advance_ray(rs, so, g, a.ray_offset);
+        s_nidx[threadIdx.x] = rs.nidx;
+      }
     }
+    // a recording tile leaves together (its barriers), after the last interaction has fed the counters
+    if (RECORD ? !any_alive : !alive) break;
   }
 
   // counters: warp-reduce, one atomic per warp and counter
+  const StepCounters sc_ctr = {s_ctr0[threadIdx.x], s_ctr1[threadIdx.x]};
   unsigned long long vals[11] = {valid ? 1ull : 0ull,
                                  sc_ctr.w0 & 0xffffu,
                                  sc_ctr.w0 >> 16,
@@ -239,30 +262,50 @@ __global__ void gen_offsets_kernel(long long* gen_offsets, int generation_limit)
   }
 }
 
-// one block per tile: copy each of the tile's runs to its final frame rows
+// one block per tile: expand each of the tile's runs of staged records into its final frame rows
+// (_RayTraceDataframe.insert, pyrayt/_pyrayt.py:168-186: current metadata, surface id, start point, end
+// point = start + direction * distance (:404-407), unit tilt (:177)).  Same functions and the same
+// -fmad=false arithmetic as the trace kernel, so the columns are bit-identical to computing them there.
 template <int LAYOUT>
-__global__ void __launch_bounds__(kTileRays) gather_kernel(const double* stage, long long capacity,
-                                                           const long long* run_start, const int* run_count,
-                                                           const long long* run_base, long long n_tiles,
-                                                           const long long* gen_offsets, int generation_limit,
-                                                           double* frame, long long frame_stride) {
+__global__ void __launch_bounds__(kTileRays) gather_kernel(const GatherArgs a) {
   const long long tile = blockIdx.x;
-  for (int g = 0; g < generation_limit; ++g) {
-    const long long idx = (long long)g * n_tiles + tile;
-    const int c = run_count[idx];
+  const Leaf* leaves =
+      reinterpret_cast<const Leaf*>(a.blob + reinterpret_cast<const BlobHeader*>(a.blob)->off_leaves);
+  for (int g = 0; g < a.generation_limit; ++g) {
+    const long long idx = (long long)g * a.n_tiles + tile;
+    const int c = a.run_count[idx];
     if (c == 0) continue;
     if ((int)threadIdx.x < c) {
-      const long long src = run_start[idx] + threadIdx.x;
-      const long long dst = gen_offsets[g] + run_base[idx] + threadIdx.x;
-      double v[kFrameCols];
+      const long long src = a.run_start[idx] + threadIdx.x;
+      const long long dst = a.gen_offsets[g] + a.run_base[idx] + threadIdx.x;
+      if (dst >= a.frame_capacity) continue;
+      double s[kStageCols];
 #pragma unroll
-      for (int k = 0; k < kFrameCols; ++k) v[k] = __ldcs(stage + k * capacity + src);
+      for (int k = 0; k < kStageCols; ++k) s[k] = __ldcs(a.stage + k * a.capacity + src);
+      const long long meta = __double_as_longlong(s[8]);
+      const long long ray = tile * kTileRays + (meta >> 32);
+      const Leaf& L = leaves[(int)(meta & 0xffffffffll)];
+      double v[kFrameCols];
+      v[0] = (g == 0) ? a.rays[8 * a.ray_stride + ray] : (double)g;  // :440-441
+      v[1] = a.rays[9 * a.ray_stride + ray];
+      v[2] = a.rays[10 * a.ray_stride + ray];
+      v[3] = s[7];
+      v[4] = a.rays[12 * a.ray_stride + ray];
+      v[5] = L.sid;
+      v[6] = s[0];
+      v[7] = s[1];
+      v[8] = s[2];
+      v[9] = s[0] + s[3] * s[6];
+      v[10] = s[1] + s[4] * s[6];
+      v[11] = s[2] + s[5] * s[6];
+      const double vn = sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);  // as step_speed
+      unit_tilt(s[3], s[4], s[5], vn, v[12], v[13], v[14]);
       if (LAYOUT == 0) {
 #pragma unroll
-        for (int k = 0; k < kFrameCols; ++k) __stcs(frame + k * frame_stride + dst, v[k]);
+        for (int k = 0; k < kFrameCols; ++k) __stcs(a.frame + k * a.frame_stride + dst, v[k]);
       } else {
 #pragma unroll
-        for (int k = 0; k < kFrameCols; ++k) frame[dst * kFrameCols + k] = v[k];
+        for (int k = 0; k < kFrameCols; ++k) a.frame[dst * kFrameCols + k] = v[k];
       }
     }
   }
@@ -612,17 +655,12 @@ cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long
   return cudaGetLastError();
 }
 
-cudaError_t prt_launch_gather(const double* stage, long long capacity, const long long* run_start,
-                              const int* run_count, const long long* run_base, long long n_tiles,
-                              const long long* gen_offsets, int generation_limit, double* frame,
-                              long long frame_stride, int layout, cudaStream_t st) {
-  if (n_tiles == 0) return cudaSuccess;
+cudaError_t prt_launch_gather(const prt::GatherArgs* a, int layout, cudaStream_t st) {
+  if (a->n_tiles == 0) return cudaSuccess;
   if (layout == 0)
-    prt::gather_kernel<0><<<(unsigned)n_tiles, prt::kTileRays, 0, st>>>(
-        stage, capacity, run_start, run_count, run_base, n_tiles, gen_offsets, generation_limit, frame, frame_stride);
+    prt::gather_kernel<0><<<(unsigned)a->n_tiles, prt::kTileRays, 0, st>>>(*a);
   else
-    prt::gather_kernel<1><<<(unsigned)n_tiles, prt::kTileRays, 0, st>>>(
-        stage, capacity, run_start, run_count, run_base, n_tiles, gen_offsets, generation_limit, frame, frame_stride);
+    prt::gather_kernel<1><<<(unsigned)a->n_tiles, prt::kTileRays, 0, st>>>(*a);
   return cudaGetLastError();
 }
 

@@ -21,9 +21,18 @@ constexpr int kTileRays = PRT_TILE;  // rays per tile == threads per block of th
 constexpr int kMaxSlots = 32;      // PRT_MAX_SLOTS
 constexpr int kMaxDepth = 6;       // simultaneously live hit lists while evaluating one component
 constexpr int kFrameCols = 15;
+// A staged record (trace kernel -> ordering pass) holds what only the trace knows about a row: start
+// position (3), direction as traced (3), hit distance, refractive index before the interaction, and one
+// word with the leaf hit and the ray's slot in its tile.  The ordering pass rebuilds the 15 frame columns
+// from it, bit for bit (same functions, same -fmad=false arithmetic): 72 instead of 120 bytes per row.
+constexpr int kStageCols = 9;  // PRT_STAGE_COLS
 // slack (world units) of the exact component pruning: hit parameters and box parameters of the
 // same point differ by rounding only (~1e-13 at scene scale), the ray offset is 1e-6
 constexpr double kCullMargin = 1e-7;
+// Scenes with more boxed components than this are traversed in ray order (OrderEntry tables + bisection).
+// Smaller scenes keep the list-order loop: every lane of a warp then looks at the same component in the same
+// iteration, which keeps the primitive switch uniform when the few components are of different kinds.
+constexpr int kOrderedMinBoxed = 8;
 
 enum OpKind : int {
   OP_LEAF = 0,        // a = leaf              : push the leaf's hit pair
@@ -62,6 +71,16 @@ struct Op {
   int kind, a, b, c;
 };
 
+// One entry of a traversal table.  For each of the six (axis k, direction sign s) pairs the components that
+// carry a proven / conservative root box ("boxed": Comp.flags & 5) are listed in the order a ray travelling
+// along that axis meets them: ascending near face in the signed coordinate u = x_k (s = 0, ray towards +k)
+// or u = -x_k (s = 1).  pmfar_u is the running maximum of far_u over the entries up to and including this
+// one, so "everything before here lies behind the ray" is a bisection on a monotone column.
+struct OrderEntry {
+  double near_u, far_u, pmfar_u;
+  int comp, pad;
+};
+
 struct Leaf {
   double m[12];    // rows 0..2 of the world->object 4x4 (row-major 3x4)
   double prm[6];   // primitive parameters (see prt_prim)
@@ -84,7 +103,15 @@ struct BlobHeader {
   int flags;       // bit 0: every bounding-box span is 0 or in [2^-823, 2^677) (fast slab test allowed)
                    // bit 1: some component has SHAPE_GENERIC (needs the interpreter kernel variant)
                    // bit 2: every component root box lies within +-1e6 (dominant-axis quick prune allowed)
+                   // bit 3: walk the boxed components in the order the ray meets them (many components);
+                   //        otherwise visit every component in list order, in lockstep across the warp
   int off_comps;   // Comp[n_components]
+  int n_boxed;     // entries per traversal table
+  int n_unboxed;   // components without a usable box: always evaluated
+  int off_order;   // OrderEntry[6][n_boxed], table index 2 * axis + sign
+  int off_unboxed; // int[n_unboxed]
+  int off_bycomp;  // OrderEntry[6][n_components]: the same entries in list order (unboxed: near -inf, far +inf)
+  int pad1, pad2;
 };
 
 // arguments of the trace kernel (filled by prt_trace)
@@ -104,6 +131,24 @@ struct TraceArgs {
   int* run_count;
   long long n_tiles;
   prt_counters* ctr;
+};
+
+// arguments of the ordering pass (gather_kernel), filled by prt_gather_frame
+struct GatherArgs {
+  const unsigned char* blob;  // scene blob in device memory (leaf -> surface id)
+  const double* rays;         // the traced RaySet: generation / intensity / wavelength / id columns come from it
+  long long n_rays, ray_stride;
+  const double* stage;
+  long long capacity;
+  const long long* run_start;
+  const int* run_count;
+  const long long* run_base;
+  long long n_tiles;
+  const long long* gen_offsets;
+  int generation_limit;
+  double* frame;
+  long long frame_stride;
+  long long frame_capacity;   // rows the frame can hold (rows beyond it are not written)
 };
 
 // arguments of the wavefront driver (prt_wavefront.cu), filled by prt_trace_wavefront

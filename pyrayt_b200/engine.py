@@ -127,7 +127,7 @@ class Engine:
         if mode != _lib.RECORD_NONE and not zero_copy and k1_events is None and method != "single":
             rows_guess = capacity if capacity is not None else min(n * G, n * self.rows_per_ray_hint * 1.05)
             total = torch.cuda.get_device_properties(self.device).total_memory
-            if method == "wavefront" or 2 * 8 * _lib.FRAME_COLS * rows_guess > 0.8 * total:
+            if method == "wavefront" or 8 * (_lib.STAGE_COLS + _lib.FRAME_COLS) * rows_guess > 0.8 * total:
                 return self.trace_wavefront(d_rays, generation_limit=G, ray_offset=ray_offset, record=record,
                                             detector_sid=detector_sid, capacity=capacity, to_host=to_host,
                                             host_frame=host_frame, host_rays=host_rays, lean=lean)
@@ -148,8 +148,9 @@ class Engine:
                 raise _lib.PrtError("generation_limit x tiles too large for one call; trace the rays in chunks")
             cap = int(capacity) if capacity is not None else int(min(n * G, max(n * self.rows_per_ray_hint * 1.05, 4096)))
             cap = max(cap, 1)
+            late_gather = to_host and zero_copy  # the gather writes into a host frame sized from the row count
             while True:
-                stage = self._buf("stage", _lib.FRAME_COLS * cap, torch.float64)
+                stage = self._buf("stage", _lib.STAGE_COLS * cap, torch.float64)
                 run_start = self._buf("run_start", G * n_tiles, torch.int64)
                 run_count = self._buf("run_count", G * n_tiles, torch.int32)
                 run_base = self._buf("run_base", G * n_tiles, torch.int64)
@@ -166,20 +167,44 @@ class Engine:
                 _lib.check(self.lib.prt_scan_runs(ctypes.byref(rec), G, gen_off.data_ptr(), self._stream()),
                            "prt_scan_runs")
                 launches += 2
+                frame = None
+                if not late_gather:
+                    # the ordering pass is enqueued before anything is read back: the frame is sized like the
+                    # staging buffer (rows <= cap whenever nothing was dropped), the kernel takes the row
+                    # offsets from device memory, and the step has one host synchronisation, at its end
+                    frame = torch.empty((_lib.FRAME_COLS, cap), dtype=torch.float64, device=self._dev())
+                    self._gather_into(rec, d_rays, G, gen_off, frame, cap)
+                    launches += 1
                 host = torch.cat([ctr, gen_off[: G + 1]]).cpu()  # one small D2H + sync
                 counters = dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in host[: len(_lib.COUNTER_FIELDS)])))
                 goff = host[_lib.COUNTER_WORDS:].numpy()
                 if counters["rows_dropped"] == 0:
                     break
                 # staging overflowed: the kernel kept counting; retry once with the exact size
+                frame = None
                 cap = int(counters["rows_reserved"])
             rows = int(goff[G])
             if n > 0:
                 self.rows_per_ray_hint = max(self.rows_per_ray_hint, rows / n)
             gen_counts = np.diff(goff).astype(np.int64)
-            frame = self._gather(rec, G, gen_off, rows, to_host, host_frame, zero_copy, goff, d_rays, host_rays, lean)
-            launches += 1 if rows else 0
+            if late_gather:
+                frame = self._gather(rec, G, gen_off, rows, to_host, host_frame, zero_copy, goff, d_rays, host_rays, lean)
+                launches += 1 if rows else 0
+            elif rows == 0:
+                frame = torch.empty((_lib.FRAME_COLS, 0), dtype=torch.float64, device=None if to_host else self._dev())
+            else:
+                frame = frame[:, :rows]
+                if to_host:
+                    frame = self._frame_to_host(frame, rows, goff, d_rays, host_frame, host_rays, lean)
             return TraceResult(frame, rows, counters, gen_counts, launches, self.n_leaves)
+
+    def _gather_into(self, rec, d_rays, G, gen_off, frame, frame_capacity, layout: int = 0):
+        """prt_gather_frame: expand the staged records of `rec` into `frame` (device or pinned host)."""
+        n = int(d_rays.shape[1])
+        _lib.check(self.lib.prt_gather_frame(self._handle, ctypes.byref(rec), d_rays.data_ptr(), n,
+                                             int(d_rays.stride(0)) if n else 0, G, gen_off.data_ptr(),
+                                             frame.data_ptr(), int(frame.stride(0)), int(frame_capacity), layout,
+                                             self._stream()), "prt_gather_frame")
 
     # ------------------------------------------------------------------ large ray sets: one generation per launch
     WAVEFRONT_MIN_RAYS = 1 << 18
@@ -327,7 +352,7 @@ class Engine:
             "n": n, "G": G, "cap": cap, "meta": meta, "run_count": run_count,
             "run_start": torch.zeros(G * n_tiles, dtype=torch.int64, device=dev),
             "run_base": torch.zeros(G * n_tiles, dtype=torch.int64, device=dev),
-            "stage": torch.empty(_lib.FRAME_COLS * cap, dtype=torch.float64, device=dev),
+            "stage": torch.empty(_lib.STAGE_COLS * cap, dtype=torch.float64, device=dev),
             "frame": torch.zeros((_lib.FRAME_COLS, cap), dtype=torch.float64, device=dev),
             "h_meta": torch.zeros(_lib.COUNTER_WORDS + G + 1, dtype=torch.int64).pin_memory(),
             "h_frame": torch.zeros((_lib.FRAME_COLS, cap), dtype=torch.float64).pin_memory(),
@@ -349,8 +374,7 @@ class Engine:
                                       ctypes.byref(st["rec"]), meta.data_ptr(), stream), "prt_trace")
         gen_off = meta[_lib.COUNTER_WORDS:]
         _lib.check(self.lib.prt_scan_runs(ctypes.byref(st["rec"]), G, gen_off.data_ptr(), stream), "prt_scan_runs")
-        _lib.check(self.lib.prt_gather_frame(ctypes.byref(st["rec"]), G, gen_off.data_ptr(), st["frame"].data_ptr(),
-                                             st["cap"], 0, stream), "prt_gather_frame")
+        self._gather_into(st["rec"], rays, G, gen_off, st["frame"], st["cap"])
         st["h_meta"].copy_(meta, non_blocking=True)
         st["h_frame"].copy_(st["frame"], non_blocking=True)
 
@@ -452,13 +476,11 @@ class Engine:
             out = host_frame if host_frame is not None else torch.empty(
                 (_lib.FRAME_COLS, rows), dtype=torch.float64, pin_memory=True)
             assert out.is_pinned() and out.shape[0] == _lib.FRAME_COLS and out.shape[1] >= rows
-            _lib.check(self.lib.prt_gather_frame(ctypes.byref(rec), G, gen_off.data_ptr(), out.data_ptr(),
-                                                 int(out.stride(0)), 0, self._stream()), "prt_gather_frame")
+            self._gather_into(rec, d_rays, G, gen_off, out, rows)
             torch.cuda.current_stream(self.device).synchronize()
             return out[:, :rows]
         frame = torch.empty((_lib.FRAME_COLS, rows), dtype=torch.float64, device=self._dev())
-        _lib.check(self.lib.prt_gather_frame(ctypes.byref(rec), G, gen_off.data_ptr(), frame.data_ptr(), rows, 0,
-                                             self._stream()), "prt_gather_frame")
+        self._gather_into(rec, d_rays, G, gen_off, frame, rows)
         if not to_host:
             return frame
         return self._frame_to_host(frame, rows, goff, d_rays, host_frame, host_rays, lean)

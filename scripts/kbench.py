@@ -18,6 +18,12 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 22
 wl = workloads.WORKLOADS[name]
 eng = pyrayt_b200.Engine(wl.scene(), 0)
 rays = wl.source.generate(n, device=0)
+if os.environ.get("KBENCH_ONLY") == "k1":  # profiling runs: three recording traces and nothing else
+    for it in range(3):
+        res = eng.trace(rays, generation_limit=wl.generation_limit)
+        torch.cuda.synchronize()
+        del res
+    sys.exit(0)
 for mode in (("all", "none") if os.environ.get("KBENCH_ONLY") != "wave" else ()):
     ts = []
     for it in range(5):
@@ -34,7 +40,7 @@ for mode in (("all", "none") if os.environ.get("KBENCH_ONLY") != "wave" else ())
     print(f"{os.environ.get('PYRAYT_B200_LIB', 'default'):40s} {name} n={n} record={mode:4s} K1 {t:8.3f} ms  "
           f"{n / t / 1e3:8.2f} Mrays/s  rows {res.rows} gens {res.counters['generations']}", flush=True)
 ts = []
-for it in range(5):
+for it in range(5 if os.environ.get("KBENCH_WAVE") else 0):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev = []
     e0.record()
@@ -43,9 +49,10 @@ for it in range(5):
     torch.cuda.synchronize()
     ts.append((e0.elapsed_time(e1), sum(a.elapsed_time(b) for a, b in ev)))
     del res
-t, ta = sorted(ts[1:])[len(ts[1:]) // 2]
-print(f"{os.environ.get('PYRAYT_B200_LIB', 'default'):40s} {name} n={n} wavefront whole step {t:8.3f} ms  "
-      f"{n / t / 1e3:8.2f} Mrays/s  (nearest-hit kernels {ta:8.3f} ms)", flush=True)
+if ts:
+    t, ta = sorted(ts[1:])[len(ts[1:]) // 2]
+    print(f"{os.environ.get('PYRAYT_B200_LIB', 'default'):40s} {name} n={n} wavefront whole step {t:8.3f} ms  "
+          f"{n / t / 1e3:8.2f} Mrays/s  (nearest-hit kernels {ta:8.3f} ms)", flush=True)
 ts = []
 for it in range(4 if os.environ.get("KBENCH_ONLY") != "wave" else 0):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

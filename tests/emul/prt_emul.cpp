@@ -6,6 +6,7 @@
 // or call this; `pytest -m "not gpu"` builds it into tests/emul/libprt_emul.so.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,12 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   std::vector<int> slots;
   std::string err;
   if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
+  // PRT_EMUL_TRAVERSAL=ordered|list forces one of nearest_hit's two traversals (the encoder picks by scene size)
+  if (const char* force = std::getenv("PRT_EMUL_TRAVERSAL")) {
+    prt::BlobHeader* h = reinterpret_cast<prt::BlobHeader*>(blob.data());
+    if (force[0] == 'o') h->flags |= 8;
+    if (force[0] == 'l') h->flags &= ~8;
+  }
   const prt::SceneView sc = prt::make_view(blob.data());
   long long total = 0;
   prt::StepCounters c = {0, 0};

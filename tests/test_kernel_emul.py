@@ -48,6 +48,24 @@ def test_component_intersect_equals_oracle(seed):
         assert np.array_equal(esid, osid)
 
 
+@pytest.mark.parametrize("traversal", ["ordered", "list"])
+def test_both_traversals_of_the_nearest_hit_search(traversal, monkeypatch):
+    """nearest_hit walks the boxed components in ray order (large scenes) or in list order (small ones);
+    the encoder picks by scene size.  Both are forced here on every golden case and on random scenes
+    (unboxed components, generic trees, ties) and must give the oracle's frame bit for bit."""
+    monkeypatch.setenv("PRT_EMUL_TRAVERSAL", traversal)
+    for name in GOLDEN_CASES:
+        scene, rays, _, gl = load_case(name)
+        want, _ = oracle.trace(scene, rays, gl)
+        got, _ = emul.trace(scene, rays, gl)
+        assert np.array_equal(got, want, equal_nan=True), name
+    for seed in range(2000, 2120):
+        scene, rays = su.random_scene_and_rays(seed, n_rays=128)
+        want, _ = oracle.trace(scene, rays, 12)
+        got, _ = emul.trace(scene, rays, 12)
+        assert np.array_equal(got, want, equal_nan=True), seed
+
+
 def test_closed_form_left_deep_merge_equals_streaming_merge():
     """All sorted pairs over {-inf,-2,-1,1,2,3,+inf} for A, B, C and all 9 operation pairs."""
     bad, cases = emul.selfcheck_left_deep()
@@ -70,3 +88,30 @@ def test_random_scene_stress():
                 oh, osid = oracle.intersect(scene, c, r)
                 eh, esid = emul.intersect(scene, c, r)
                 assert np.array_equal(eh, oh) and np.array_equal(esid, osid), (seed, c)
+
+
+def test_equal_distances_go_to_the_earlier_component_in_any_visiting_order():
+    """_st_propagate keeps the first component among equal distances (strict `<`, pyrayt/_pyrayt.py:384).
+    The kernel visits boxed components in the order the ray meets their boxes, so the rule is restated as
+    (smallest distance, then lowest component index): coincident surfaces in both list orders, with other
+    components before, between and behind them, hit from both sides and obliquely."""
+    def plane(x, sid, mat=su.MAT_ABSORBER):
+        return su.Leaf(su.PLANE, [4.0, 4.0], mat=mat, world=su.translate(x, 0, 0) @ su.rot_y(90), sid=sid)
+
+    def lens(x, sid):
+        a = su.Leaf(su.SPHERE, [2.0], mat=su.MAT_GLASS_CONST, matp=[1.5], world=su.translate(x + 1.9, 0, 0), sid=sid)
+        b = su.Leaf(su.SPHERE, [2.0], mat=su.MAT_GLASS_CONST, matp=[1.5], world=su.translate(x - 1.9, 0, 0), sid=sid + 1)
+        return su.intersect(a, b, aabb=(x - 0.1, x + 0.1, -0.7, 0.7, -0.7, 0.7))
+
+    origins = [[-3, 0.1, 0.05], [-3, -0.2, 0.1], [6, 0.1, 0.0], [6, 0.3, -0.2], [-3, 0.0, 0.0]]
+    dirs = [[1, 0, 0], [0.999, 0.02, 0.01], [-1, 0, 0], [-0.99, -0.05, 0.03], [1, 0, 0]]
+    dirs = [np.asarray(d) / np.linalg.norm(d) for d in dirs]
+    rays = su.make_rays(origins, dirs)
+    for first, second in ((31, 32), (32, 31)):
+        comps = [plane(5.0, 40), plane(2.0, first), lens(0.0, 50), plane(2.0, second), plane(-4.0, 44, su.MAT_MIRROR)]
+        scene = su.build(comps)
+        want, _ = oracle.trace(scene, rays, 6)
+        got, _ = emul.trace(scene, rays, 6)
+        assert np.array_equal(got, want, equal_nan=True)
+        ends = want[5][want[0] == want[0].max()]
+        assert first in set(want[5]) and second not in set(want[5]), (first, second, ends)
