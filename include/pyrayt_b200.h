@@ -307,8 +307,10 @@ typedef struct prt_source_desc {
   int32_t kind;        /* 1 = disk/field/wavelength fan (config 4), 2 = solid-angle cone (config 2),
                           3 = Lambertian cone (config 5);
                           the reference's deterministic sources (pyrayt/components.py:511-613):
-                          10 = LineOfRays, 11 = CircleOfRays, 12 = ConeOfRays, 13 = WedgeOfRays with
-                          p[0] = spacing | diameter | cone angle [rad] | wedge angle [rad], p[1] = wavelength,
+                          10 = LineOfRays, 11 = CircleOfRays, 12 = ConeOfRays, 13 = WedgeOfRays, 14 = Lamp
+                          (:616-654: the same Lambertian law driven by counter-based uniforms of `seed` and the
+                          ray id instead of NumPy's global stream; origin[0] = width, origin[1] = length) with
+                          p[0] = spacing | diameter | cone angle | wedge angle | max angle [rad], p[1] = wavelength,
                           p[2] = ray count of the source, p[3] = id of its first ray,
                           p[4..15] = rows 0..2 of the source's 4x4 world matrix; a call writes the window
                           [first_index, first_index + n_rays) of the source's p[2] rays (a rank's share of

@@ -94,7 +94,7 @@ def from_source(src, n: int, first_index: int = 0, total=None) -> np.ndarray:
     return generate(src.kind, src.seed, tuple(src.origin), list(src.p), n, first_index)
 
 
-def reference_source(kind: int, p, n: int) -> np.ndarray:
+def reference_source(kind: int, p, n: int, seed: int = 0, origin=(0.0, 0.0, 0.0)) -> np.ndarray:
     """NumPy restatement of pyrayt.components Line/Circle/Cone/WedgeOfRays.generate_rays
     (pyrayt/components.py:481-613) for the descriptor layout of pyrayt_b200.sources.from_reference:
     the same NumPy expressions as the reference, so it is bit-identical to it."""
@@ -119,6 +119,17 @@ def reference_source(kind: int, p, n: int) -> np.ndarray:
         angles = np.linspace(-p[0] / 2, p[0] / 2, n)
         rays[1, 0] = np.cos(angles)
         rays[1, 1] = np.sin(angles)
+    elif kind == 14:
+        # Lamp._local_ray_generation (pyrayt/components.py:637-654) with u01(seed, ray id, k) as the uniforms
+        rid = (np.float64(p[3]) + np.arange(n)).astype(np.uint64)
+        theta = np.arccos(1 - u01(seed, rid, 0) * (1 - np.cos(p[0])))
+        phi = u01(seed, rid, 1) * (2 * 3.141592653589793)
+        rays[0, 1] = origin[0] * (u01(seed, rid, 2) - 0.5)
+        rays[0, 2] = origin[1] * (u01(seed, rid, 3) - 0.5)
+        rays[1, 0] = np.cos(theta)
+        rays[1, 1] = np.sin(theta) * np.cos(phi)
+        rays[1, 2] = np.sin(theta) * np.sin(phi)
+        intensity = 100.0 * np.cos(theta)
     else:
         raise ValueError(kind)
     M = np.eye(4)
@@ -127,7 +138,7 @@ def reference_source(kind: int, p, n: int) -> np.ndarray:
     rays[1] /= np.linalg.norm(rays[1], axis=0)
     out = np.zeros((13, n))
     out[:8] = rays.reshape(8, n)
-    out[9] = 100.0
+    out[9] = intensity if kind == 14 else 100.0
     out[10] = p[1]
     out[11] = 1.0
     out[12] = p[3] + np.arange(n)

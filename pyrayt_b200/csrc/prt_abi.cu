@@ -331,7 +331,7 @@ int prt_generate_source(const prt_source_desc* src, double* d_rays, int64_t n_ra
                         int64_t first_index, void* cuda_stream) {
   if (!src || (!d_rays && n_rays > 0)) return fail(PRT_ERR_INVALID, "null argument");
   const bool synthetic = src->kind >= 1 && src->kind <= 3;
-  const bool reference = src->kind >= 10 && src->kind <= 13;
+  const bool reference = src->kind >= 10 && src->kind <= 14;
   if (!synthetic && !reference) return fail(PRT_ERR_INVALID, "unknown source kind");
   if (reference && (first_index < 0 || (double)(first_index + n_rays) > src->p[2]))
     return fail(PRT_ERR_INVALID, "window [first_index, first_index + n_rays) exceeds the source's ray count p[2]");

@@ -424,6 +424,98 @@ PRT_HD void sphere_pair_hits(const Leaf& A, const Leaf& B, double p0, double p1,
   sort2(b0, b1);
 }
 
+// A whole lens at once: the aperture Cylinder and the two Sphere surfaces of thick_lens / biconvex_lens
+// (pyrayt/components.py:73-198), i.e. three of leaf_hits' cases written as one straight-line block so that
+// their dependency chains (transform, quadratic, square root, reciprocal, quotients) overlap in the pipeline
+// -- the kernel is bound by dependent-issue latency, not by issue slots.  Every rare case of the literal
+// code (near-axis / perpendicular rays: the isclose branches of binomial_root and the cap clip; operands
+// the 3-instruction division cannot take) is folded into ONE predicate: when it fails nothing here is
+// used and the caller evaluates the leaves one by one with leaf_hits.  When it holds, every value below
+// is computed by the same expressions as in leaf_hits, so the result is bit-identical.
+PRT_HD bool lens3_hits_fast(const Leaf& Y, const Leaf& A, const Leaf& B, double p0, double p1, double p2, double v0,
+                            double v1, double v2, double& y0, double& y1, double& a0, double& a1, double& b0,
+                            double& b1) {
+  // world -> object (world_objects.py:367-369)
+  const double yo0 = Y.m[0] * p0 + Y.m[1] * p1 + Y.m[2] * p2 + Y.m[3];
+  const double ao0 = A.m[0] * p0 + A.m[1] * p1 + A.m[2] * p2 + A.m[3];
+  const double bo0 = B.m[0] * p0 + B.m[1] * p1 + B.m[2] * p2 + B.m[3];
+  const double yo1 = Y.m[4] * p0 + Y.m[5] * p1 + Y.m[6] * p2 + Y.m[7];
+  const double ao1 = A.m[4] * p0 + A.m[5] * p1 + A.m[6] * p2 + A.m[7];
+  const double bo1 = B.m[4] * p0 + B.m[5] * p1 + B.m[6] * p2 + B.m[7];
+  const double yo2 = Y.m[8] * p0 + Y.m[9] * p1 + Y.m[10] * p2 + Y.m[11];
+  const double ao2 = A.m[8] * p0 + A.m[9] * p1 + A.m[10] * p2 + A.m[11];
+  const double bo2 = B.m[8] * p0 + B.m[9] * p1 + B.m[10] * p2 + B.m[11];
+  const double yd0 = Y.m[0] * v0 + Y.m[1] * v1 + Y.m[2] * v2;
+  const double ad0 = A.m[0] * v0 + A.m[1] * v1 + A.m[2] * v2;
+  const double bd0 = B.m[0] * v0 + B.m[1] * v1 + B.m[2] * v2;
+  const double yd1 = Y.m[4] * v0 + Y.m[5] * v1 + Y.m[6] * v2;
+  const double ad1 = A.m[4] * v0 + A.m[5] * v1 + A.m[6] * v2;
+  const double bd1 = B.m[4] * v0 + B.m[5] * v1 + B.m[6] * v2;
+  const double yd2 = Y.m[8] * v0 + Y.m[9] * v1 + Y.m[10] * v2;
+  const double ad2 = A.m[8] * v0 + A.m[9] * v1 + A.m[10] * v2;
+  const double bd2 = B.m[8] * v0 + B.m[9] * v1 + B.m[10] * v2;
+  // the three quadratics (primitives.py:252-262, :664-667 + operations.py:39-57)
+  const double yr = Y.prm[0], ar = A.prm[0], br = B.prm[0];
+  const double ya = yd0 * yd0 + yd1 * yd1;
+  const double aa = ad0 * ad0 + ad1 * ad1 + ad2 * ad2;
+  const double ba = bd0 * bd0 + bd1 * bd1 + bd2 * bd2;
+  const double yb = 2 * (yd0 * yo0 + yd1 * yo1);
+  const double ab = 2 * (ad0 * ao0 + ad1 * ao1 + ad2 * ao2);
+  const double bb = 2 * (bd0 * bo0 + bd1 * bo1 + bd2 * bo2);
+  const double yc = (yo0 * yo0 + yo1 * yo1) - yr * yr;
+  const double ac = (ao0 * ao0 + ao1 * ao1 + ao2 * ao2) - ar * ar;
+  const double bc = (bo0 * bo0 + bo1 * bo1 + bo2 * bo2) - br * br;
+  const double ydisc = yb * yb - 4 * ya * yc;
+  const double adisc = ab * ab - 4 * aa * ac;
+  const double bdisc = bb * bb - 4 * ba * bc;
+  const double yroot = sqrt(fmax(0.0, ydisc));
+  const double aroot = sqrt(fmax(0.0, adisc));
+  const double broot = sqrt(fmax(0.0, bdisc));
+  // the literal code's rare branches: isclose(a, 0) in binomial_root, isclose(d_z, 0) in the cap clip
+  const bool rare = isz(ya) | isz(yd2);
+  const Rcp yden = make_rcp(2 * ya + 0.0);
+  const Rcp aden = make_rcp(2 * aa);
+  const Rcp bden = make_rcp(2 * ba);
+  const Rcp zden = make_rcp(yd2 + 0.0);
+  const double yn0 = -yb + yroot, yn1 = -yb - yroot;
+  const double an0 = -ab + aroot, an1 = -ab - aroot;
+  const double bn0 = -bb + broot, bn1 = -bb - broot;
+  const double zn0 = Y.prm[1] - yo2, zn1 = Y.prm[2] - yo2;
+  double s0 = div_fast(yn0, yden), s1 = div_fast(yn1, yden);
+  a0 = div_fast(an0, aden);
+  a1 = div_fast(an1, aden);
+  b0 = div_fast(bn0, bden);
+  b1 = div_fast(bn1, bden);
+  double c0 = div_fast(zn0, zden), c1 = div_fast(zn1, zden);
+  const bool ok = (exp_of(yn0) - kExpLo < yden.lim) & (exp_of(yn1) - kExpLo < yden.lim) &
+                  (exp_of(an0) - kExpLo < aden.lim) & (exp_of(an1) - kExpLo < aden.lim) &
+                  (exp_of(bn0) - kExpLo < bden.lim) & (exp_of(bn1) - kExpLo < bden.lim) &
+                  (exp_of(zn0) - kExpLo < zden.lim) & (exp_of(zn1) - kExpLo < zden.lim);
+  if (!(ydisc >= 0)) {
+    s0 = PRT_INF;
+    s1 = PRT_INF;
+  }
+  if (!(adisc >= 0)) {
+    a0 = PRT_INF;
+    a1 = PRT_INF;
+  }
+  if (!(bdisc >= 0)) {
+    b0 = PRT_INF;
+    b1 = PRT_INF;
+  }
+  sort2(s0, s1);
+  sort2(a0, a1);
+  sort2(b0, b1);
+  sort2(c0, c1);
+  // cap clip of the cylinder (primitives.py:680-712)
+  const double lo = fmax(s0, c0);
+  const double hi = fmin(s1, c1);
+  const bool hit = lo <= hi;
+  y0 = hit ? lo : PRT_INF;
+  y1 = hit ? hi : PRT_INF;
+  return ok & !rare;
+}
+
 // TracerSurface.get_world_normals (world_objects.py:401-418) with the primitives' normal()
 // (Sphere :273-296, Paraboloid :401-419, Plane :494-498, Cube :583-602, Cylinder :714-741)
 PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double& n0,
@@ -617,49 +709,74 @@ PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, d
 // ---------------------------------------------------------------- register-only left-deep components
 //
 // Every reference factory builds a left-deep tree of two or three leaves ((A op1 B) op2 C,
-// SURVEY 8(a3)).  For those shapes the streaming merge is evaluated in closed form, entirely in
-// registers: in the stable merge of two sorted lists the position of an entry is its own index
-// plus the number of entries of the other list that precede it (strictly smaller for a left
-// entry, smaller-or-equal for a right entry: the left child wins ties), and array_csg's running
-// count at that position (csg.py:41-48) depends only on the parities of those two numbers.  The
-// result is the same keep/drop decision per entry as merge_lists makes, without lists in memory.
-
-// array_csg's keep rule for an entry whose running count is `cnt` after and `prev` before it
-PRT_HD bool csg_keep(int op, int cnt, int prev) {
-  return (op == PRT_UNION) ? ((cnt != 0) != (prev != 0)) : ((cnt == 2) | (prev == 2));
-}
-
-// merge of (a0,a1) [left] with (b0,b1) [right]; +inf marks a missing entry.  Outputs keep flags
-// and the merged positions of the four entries (A0, A1, B0, B1).
-PRT_HD void merge22(int op, double a0, double a1, double b0, double b1, bool keep[4], int pos[4], bool& tie) {
-  const bool va0 = a0 < PRT_INF, va1 = a1 < PRT_INF, vb0 = b0 < PRT_INF, vb1 = b1 < PRT_INF;
-  const bool l00 = b0 < a0, l01 = b0 < a1, l10 = b1 < a0, l11 = b1 < a1;  // l[j][i] = b_j < a_i
-  const int rb0 = (int)l00 + (int)l10, rb1 = (int)l01 + (int)l11;
-  const int lb0 = (int)(va0 & !l00) + (int)(va1 & !l01), lb1 = (int)(va0 & !l10) + (int)(va1 & !l11);
-  // (bitwise logic on purpose: no short-circuit branches)
-  tie |= (va0 & vb0 & (a0 == b0)) | (va0 & vb1 & (a0 == b1)) | (va1 & vb0 & (a1 == b0)) | (va1 & vb1 & (a1 == b1));
-  const int start = (op == PRT_DIFFERENCE) ? 1 : 0;
-  const int sR = (op == PRT_DIFFERENCE) ? -1 : 1;
-  int cnt;
-  cnt = start + 1 + sR * (rb0 & 1);                 // A0: first left entry (enters)
-  keep[0] = va0 & csg_keep(op, cnt, cnt - 1);
-  cnt = start + 0 + sR * (rb1 & 1);                 // A1: second left entry (exits)
-  keep[1] = va1 & csg_keep(op, cnt, cnt + 1);
-  cnt = start + (lb0 & 1) + sR;                     // B0
-  keep[2] = vb0 & csg_keep(op, cnt, cnt - sR);
-  cnt = start + (lb1 & 1);                          // B1
-  keep[3] = vb1 & csg_keep(op, cnt, cnt + sR);
-  pos[0] = rb0;
-  pos[1] = 1 + rb1;
-  pos[2] = lb0;
-  pos[3] = 1 + lb1;
-}
+// SURVEY 8(a3)).  For those shapes the two stable merges of CSGSurface.intersect are evaluated in
+// closed form, entirely in registers.
+//
+// array_csg (csg.py:13-61) walks the merged, stably sorted entries with a counter and keeps the entries
+// at which the counter enters or leaves its "inside" value.  Entry k of a child list enters the child
+// when k is even and leaves it when k is odd (csg.py:41,:46), so the counter is a function of "inside
+// left child" and "inside right child", and the kept entries are exactly the entries at which
+// op(inside L, inside R) changes: UNION keeps zero <-> non-zero (:53-54), INTERSECT / DIFFERENCE keep
+// count == 2 and the entry after it (:57-59; DIFFERENCE starts at 1 and flips the right child's sign,
+// :45-48).  The kept entries of the first merge alternate enter / leave again, so the second merge sees
+// op1(inside A, inside B) as its left state.  The whole component therefore keeps an entry x iff
+//      F(inA, inB, inC) = op2(op1(inA, inB), inC)
+// changes at x, where the state of the *other* leaves at x follows from how many of their entries sort
+// before x (one: inside; none or both: outside), with the reference's tie order: stable sorts put the left
+// child first, i.e. A before B before C on equal keys.  F is an 8-bit truth table made by the encoder
+// (Comp.tt).  The nearest hit is the first kept entry with t > 0 in that order.  (Cross-checked against
+// the streaming merge_lists on every sorted pair over {-inf, -2, -1, 1, 2, 3, +inf} for A, B and C, all
+// nine operation pairs, with and without the inner bounding box: tests/test_kernel_emul.py.)
 
 // running best of one component: first positive kept entry in merged order
 PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
   const bool take = keep & (t > 0) & (t < ct);
   ct = take ? t : ct;
   cl = take ? leaf : cl;
+}
+
+// does F change when leaf `own` (bit mask 1 / 2 / 4) toggles, the state just before being `before`?
+PRT_HD bool tt_changes(unsigned tt, unsigned before, unsigned own) {
+  return (((tt >> before) ^ (tt >> (before ^ own))) & 1u) != 0u;
+}
+
+// (a0,a1), (b0,b1), (c0,c1): sorted hit pairs of leaves A, B, C (+inf = missing entry; LEFT2: c = +inf and
+// tt ignores C).  Returns the nearest positive kept entry (ct, cl) and whether equal keys were compared.
+PRT_HD void left_deep_first_hit(unsigned tt, double a0, double a1, double b0, double b1, double c0, double c1,
+                                int la, int lb, int lc, double& ct, int& cl, bool& tie) {
+  const bool va0 = a0 < PRT_INF, va1 = a1 < PRT_INF, vb0 = b0 < PRT_INF, vb1 = b1 < PRT_INF;
+  const bool vc0 = c0 < PRT_INF, vc1 = c1 < PRT_INF;
+  // y < x for every pair of entries of different leaves (bitwise logic on purpose: no short-circuit branches)
+  const bool b0a0 = b0 < a0, b1a0 = b1 < a0, b0a1 = b0 < a1, b1a1 = b1 < a1;
+  const bool c0a0 = c0 < a0, c1a0 = c1 < a0, c0a1 = c0 < a1, c1a1 = c1 < a1;
+  const bool c0b0 = c0 < b0, c1b0 = c1 < b0, c0b1 = c0 < b1, c1b1 = c1 < b1;
+  tie |= (va0 & vb0 & (a0 == b0)) | (va0 & vb1 & (a0 == b1)) | (va1 & vb0 & (a1 == b0)) | (va1 & vb1 & (a1 == b1)) |
+         (va0 & vc0 & (a0 == c0)) | (va0 & vc1 & (a0 == c1)) | (va1 & vc0 & (a1 == c0)) | (va1 & vc1 & (a1 == c1)) |
+         (vb0 & vc0 & (b0 == c0)) | (vb0 & vc1 & (b0 == c1)) | (vb1 & vc0 & (b1 == c0)) | (vb1 & vc1 & (b1 == c1));
+  // state of the other leaves just before each entry.  An entry y of a later leaf precedes x only when
+  // y < x; an entry y of an earlier leaf precedes x when y <= x, i.e. when !(x < y): in the XOR of a
+  // leaf's two entries the two negations cancel, so the same comparison bits serve both directions.
+  const unsigned inB_a0 = (unsigned)(b0a0 ^ b1a0), inB_a1 = (unsigned)(b0a1 ^ b1a1);
+  const unsigned inC_a0 = (unsigned)(c0a0 ^ c1a0), inC_a1 = (unsigned)(c0a1 ^ c1a1);
+  const unsigned inA_b0 = (unsigned)(b0a0 ^ b0a1), inA_b1 = (unsigned)(b1a0 ^ b1a1);
+  const unsigned inC_b0 = (unsigned)(c0b0 ^ c1b0), inC_b1 = (unsigned)(c0b1 ^ c1b1);
+  const unsigned inA_c0 = (unsigned)(c0a0 ^ c0a1), inA_c1 = (unsigned)(c1a0 ^ c1a1);
+  const unsigned inB_c0 = (unsigned)(c0b0 ^ c0b1), inB_c1 = (unsigned)(c1b0 ^ c1b1);
+  // entry 0 of a leaf enters it (own bit 0 -> 1), entry 1 leaves it (1 -> 0)
+  const bool ka0 = va0 & tt_changes(tt, (inB_a0 << 1) | (inC_a0 << 2), 1u);
+  const bool ka1 = va1 & tt_changes(tt, 1u | (inB_a1 << 1) | (inC_a1 << 2), 1u);
+  const bool kb0 = vb0 & tt_changes(tt, inA_b0 | (inC_b0 << 2), 2u);
+  const bool kb1 = vb1 & tt_changes(tt, inA_b1 | 2u | (inC_b1 << 2), 2u);
+  const bool kc0 = vc0 & tt_changes(tt, inA_c0 | (inB_c0 << 1), 4u);
+  const bool kc1 = vc1 & tt_changes(tt, inA_c1 | (inB_c1 << 1) | 4u, 4u);
+  ct = PRT_INF;
+  cl = -1;
+  take_hit(ka0, a0, la, ct, cl);
+  take_hit(ka1, a1, la, ct, cl);
+  take_hit(kb0, b0, lb, ct, cl);
+  take_hit(kb1, b1, lb, ct, cl);
+  take_hit(kc0, c0, lc, ct, cl);
+  take_hit(kc1, c1, lc, ct, cl);
 }
 
 // The ray's dominant axis, for the ordered traversal of the boxed components (nearest_hit).  Along one
@@ -705,14 +822,32 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
     inner_hit = b0 < PRT_INF;
   }
   const int la = C.leaf_a, lb = C.leaf_b, lc = C.leaf_c;
-  const int op1 = C.op1, op2 = C.op2;
   double a0 = PRT_INF, a1 = PRT_INF, q0 = PRT_INF, q1 = PRT_INF, c0 = PRT_INF, c1 = PRT_INF;
   // one (not unrolled) loop over the leaves keeps a single copy of leaf_hits in the hot loop
   // Lenses carry two spherical surfaces ((aperture, sphere, sphere) for thick_lens, (sphere, sphere,
   // aperture) for biconvex_lens): those two leaves are evaluated side by side (see sphere_pair_hits),
   // the remaining leaf by the loop below.  `todo` = bit k set: leaf k still to be evaluated.
   unsigned todo = inner_hit ? ((shape == SHAPE_LEFT3) ? 7u : 3u) : 4u;
-  if (inner_hit) {
+#ifndef PRT_NO_LENS3
+  if (inner_hit & ((C.flags & 24) != 0)) {
+    // a lens: capped Cylinder + two Spheres, the cylinder first (thick_lens, bit 3) or last (biconvex_lens, bit 4)
+    const bool cyl_first = (C.flags & 8) != 0;
+    const Leaf& Y = sc.leaves[cyl_first ? la : lc];
+    const Leaf& A = sc.leaves[cyl_first ? lb : la];
+    const Leaf& B = sc.leaves[cyl_first ? lc : lb];
+    double y0, y1, s0, s1, u0, u1;
+    if (lens3_hits_fast(Y, A, B, p0, p1, p2, v0, v1, v2, y0, y1, s0, s1, u0, u1)) {
+      a0 = cyl_first ? y0 : s0;
+      a1 = cyl_first ? y1 : s1;
+      q0 = cyl_first ? s0 : u0;
+      q1 = cyl_first ? s1 : u1;
+      c0 = cyl_first ? u0 : y0;
+      c1 = cyl_first ? u1 : y1;
+      todo = 0u;
+    }
+  }
+#endif
+  if (inner_hit & (todo != 0u)) {
     const int ta = sc.leaves[la].type, tb = sc.leaves[lb].type;
     const int tc = (shape == SHAPE_LEFT3) ? sc.leaves[lc].type : 0;
     if ((tb == PRT_SPHERE) & (tc == PRT_SPHERE)) {
@@ -740,49 +875,8 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
       c1 = t1;
     }
   }
-  bool keep[4] = {false, false, false, false};
-  int pos[4] = {0, 1, 2, 3};
-  if (inner_hit) merge22(op1, a0, a1, q0, q1, keep, pos, tie);
-  if (shape == SHAPE_LEFT2) {
-    take_hit(keep[0], a0, la, ct, cl);
-    take_hit(keep[1], a1, la, ct, cl);
-    take_hit(keep[2], q0, lb, ct, cl);
-    take_hit(keep[3], q1, lb, ct, cl);
-    return;
-  }
-  // second merge: left = the kept entries of the first merge (index = number of kept entries before
-  // them in merged order), right = leaf c
-  const double x[4] = {a0, a1, q0, q1};
-  unsigned km = 0;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) km |= keep[e] ? (1u << pos[e]) : 0u;
-  const bool vc0 = c0 < PRT_INF, vc1 = c1 < PRT_INF;
-  const int start = (op2 == PRT_DIFFERENCE) ? 1 : 0;
-  const int sR = (op2 == PRT_DIFFERENCE) ? -1 : 1;
-  int lb0 = 0, lb1 = 0;
-  bool keep2[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const bool l0 = c0 < x[e], l1 = c1 < x[e];
-    const int rb = (int)l0 + (int)l1;
-    lb0 += (int)(keep[e] & !l0);
-    lb1 += (int)(keep[e] & !l1);
-    tie |= keep[e] & ((vc0 & (x[e] == c0)) | (vc1 & (x[e] == c1)));
-    const int idx = popc32(km & ((1u << pos[e]) - 1u));
-    const int up = (idx & 1) ? -1 : 1;  // even index enters
-    const int cnt = start + ((idx + 1) & 1) + sR * (rb & 1);
-    keep2[e] = keep[e] & csg_keep(op2, cnt, cnt - up);
-  }
-  int cnt = start + (lb0 & 1) + sR;
-  const bool kc0 = vc0 & csg_keep(op2, cnt, cnt - sR);
-  cnt = start + (lb1 & 1);
-  const bool kc1 = vc1 & csg_keep(op2, cnt, cnt + sR);
-  take_hit(keep2[0], a0, la, ct, cl);
-  take_hit(keep2[1], a1, la, ct, cl);
-  take_hit(keep2[2], q0, lb, ct, cl);
-  take_hit(keep2[3], q1, lb, ct, cl);
-  take_hit(kc0, c0, lc, ct, cl);
-  take_hit(kc1, c1, lc, ct, cl);
+  // a missed inner box empties (A op1 B) whatever the leaves say (csg.py:126-133): a0..q1 are still +inf
+  left_deep_first_hit((unsigned)C.tt, a0, a1, q0, q1, c0, c1, la, lb, lc, ct, cl, tie);
 }
 
 // nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386).  The reference visits the

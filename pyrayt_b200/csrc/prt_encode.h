@@ -240,6 +240,19 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
         for (int k = 0; k < 6; ++k) C.root_box[k] = enc.aabb[6 * o[0].a + k];
         for (int k = 0; k < 6; ++k) C.inner_box[k] = enc.aabb[6 * o[1].a + k];
       }
+      if (shape == prt::SHAPE_LEFT2 || shape == prt::SHAPE_LEFT3) {
+        auto apply = [](int op, int x, int y) { return op == PRT_UNION ? (x | y) : (op == PRT_INTERSECT ? (x & y) : (x & (y ^ 1))); };
+        for (int bits = 0; bits < 8; ++bits) {
+          const int f1 = apply(C.op1, bits & 1, (bits >> 1) & 1);
+          const int f = (shape == prt::SHAPE_LEFT3) ? apply(C.op2, f1, (bits >> 2) & 1) : f1;
+          C.tt |= f << bits;
+        }
+      }
+      if (shape == prt::SHAPE_LEFT3) {
+        const int ta = d->leaf_type[C.leaf_a], tb = d->leaf_type[C.leaf_b], tc = d->leaf_type[C.leaf_c];
+        if (ta == PRT_CYLINDER && tb == PRT_SPHERE && tc == PRT_SPHERE) C.flags |= 8;
+        if (ta == PRT_SPHERE && tb == PRT_SPHERE && tc == PRT_CYLINDER) C.flags |= 16;
+      }
       // convex solids: intersections of convex primitives (every leaf type but the flat Plane)
       if (shape == prt::SHAPE_LEFT2 || shape == prt::SHAPE_LEFT3) {
         bool convex = C.op1 == PRT_INTERSECT && (shape == prt::SHAPE_LEFT2 || C.op2 == PRT_INTERSECT);

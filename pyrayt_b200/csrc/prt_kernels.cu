@@ -533,7 +533,7 @@ __global__ void reference_source_kernel(const prt_source_desc src, double* rays,
   if (w >= count) return;
   const long long j = first + w;
   const double jd = (double)j, nd = (double)n;
-  double lx = 0, ly = 0, lz = 0, ux = 0, uy = 0, uz = 0;
+  double lx = 0, ly = 0, lz = 0, ux = 0, uy = 0, uz = 0, inten = 100.0;
   const double two_pi = 2 * 3.141592653589793;
   if (src.kind == 10) {  // LineOfRays: y = linspace(-s/2, s/2, n), direction +x
     if (n > 1) {
@@ -558,6 +558,20 @@ __global__ void reference_source_kernel(const prt_source_desc src, double* rays,
       uz = sin(src.p[0]) * cos(ang);
     }
     ux = cos(src.p[0]);
+  } else if (src.kind == 14) {
+    // Lamp / StaticLamp (pyrayt/components.py:616-662, _sphere_sample :56-70): same law -- theta =
+    // arccos(1 - u (1 - cos max_angle)), phi = 2 pi u', start point uniform on the width x length rectangle,
+    // intensity 100 cos(theta) -- with the counter-based uniforms u01(seed, ray id, k) in place of NumPy's
+    // global Mersenne-Twister stream (opt-in: RayTracer.lamp_seed; origin[0] = width, origin[1] = length)
+    const unsigned long long rid = (unsigned long long)(src.p[3] + jd);
+    const double theta = acos(1 - u01(src.seed, rid, 0) * (1 - cos(src.p[0])));
+    const double phi = u01(src.seed, rid, 1) * two_pi;
+    ly = src.origin[0] * (u01(src.seed, rid, 2) - 0.5);
+    lz = src.origin[1] * (u01(src.seed, rid, 3) - 0.5);
+    ux = cos(theta);
+    uy = sin(theta) * cos(phi);
+    uz = sin(theta) * sin(phi);
+    inten = 100.0 * cos(theta);
   } else {  // 13 WedgeOfRays: angles = linspace(-a/2, a/2, n)
     double ang;
     if (n > 1) {
@@ -591,7 +605,7 @@ __global__ void reference_source_kernel(const prt_source_desc src, double* rays,
   r[6 * stride] = dz;
   r[7 * stride] = 0.0;
   r[8 * stride] = 0.0;
-  r[9 * stride] = 100.0;
+  r[9 * stride] = inten;
   r[10 * stride] = src.p[1];
   r[11 * stride] = 1.0;
   r[12 * stride] = src.p[3] + jd;

@@ -59,10 +59,14 @@ struct Comp {
                // bit 1: the solid is convex (INTERSECT of convex primitives): a ray that has just left
                //        it through one of its faces cannot hit it again before it changes direction
                // bit 2: SHAPE_LEAF only: root_box is a conservative world box of the bare surface (quick prune)
+               // bit 3 / 4: SHAPE_LEFT3 of a capped Cylinder and two Spheres with the cylinder as leaf a (bit 3,
+               //        thick_lens) or leaf c (bit 4, biconvex_lens): evaluated in one block by lens3_hits_fast
   int begin, end;                  // ops [begin, end)
   int leaf_a, leaf_b, leaf_c;      // SHAPE_LEAF: leaf_a; SHAPE_LEFT2: a, b; SHAPE_LEFT3: a, b, c
   int op1, op2;                    // (A op1 B) op2 C
-  int pad[3];
+  int tt;                          // truth table of F(inA, inB, inC) = op2(op1(inA, inB), inC), bit a | b<<1 | c<<2
+                                   // (SHAPE_LEFT2: op1(inA, inB)); see left_deep_first_hit
+  int pad[2];
   double root_box[6];
   double inner_box[6];             // SHAPE_LEFT3: box of (A op1 B)
 };

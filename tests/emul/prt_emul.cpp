@@ -134,19 +134,31 @@ int prt_emul_prune_flags(const prt_scene_desc* d, int* flags) {
   return 0;
 }
 
-// Exhaustive cross-check of the closed-form left-deep evaluation (merge22 + the second merge of
-// eval_left_deep) against the streaming merge_lists on small sorted pairs with ties, -inf and
-// +inf entries: returns the number of disagreements in the selected first-positive hit.
+// Exhaustive cross-check of the closed-form left-deep evaluation (left_deep_first_hit with the encoder's
+// truth tables) against the streaming merge_lists on small sorted pairs with ties, -inf and +inf
+// entries: returns the number of disagreements in the selected first-positive hit (or a tie the
+// streaming merge saw and the closed form did not report).
 long long prt_emul_selfcheck_left_deep(long long* cases_out) {
   const double V[] = {-INFINITY, -2.0, -1.0, 1.0, 2.0, 3.0, INFINITY};
   const int nv = 7;
   long long bad = 0, cases = 0;
+  auto apply = [](int op, int x, int y) { return op == PRT_UNION ? (x | y) : (op == PRT_INTERSECT ? (x & y) : (x & (y ^ 1))); };
   for (int op1 = 1; op1 <= 3; ++op1)
-    for (int op2 = 1; op2 <= 3; ++op2)
+    for (int op2 = 1; op2 <= 3; ++op2) {
+      unsigned tt2 = 0, tt3 = 0;  // as prt_encode.h builds Comp.tt for SHAPE_LEFT2 / SHAPE_LEFT3
+      for (int bits = 0; bits < 8; ++bits) {
+        const int f1 = apply(op1, bits & 1, (bits >> 1) & 1);
+        tt2 |= (unsigned)f1 << bits;
+        tt3 |= (unsigned)apply(op2, f1, (bits >> 2) & 1) << bits;
+      }
       for (int ia0 = 0; ia0 < nv; ++ia0) for (int ia1 = ia0; ia1 < nv; ++ia1)
       for (int ib0 = 0; ib0 < nv; ++ib0) for (int ib1 = ib0; ib1 < nv; ++ib1)
-      for (int ic0 = 0; ic0 < nv; ++ic0) for (int ic1 = ic0; ic1 < nv; ++ic1) {
-        const double a[2] = {V[ia0], V[ia1]}, b[2] = {V[ib0], V[ib1]}, c[2] = {V[ic0], V[ic1]};
+      for (int ic0 = 0; ic0 < nv; ++ic0) for (int ic1 = ic0; ic1 < nv; ++ic1)
+      for (int inner = 0; inner < 2; ++inner) {  // inner = 0: the box of (A op1 B) was missed
+        const double a[2] = {inner ? V[ia0] : INFINITY, inner ? V[ia1] : INFINITY};
+        const double b[2] = {inner ? V[ib0] : INFINITY, inner ? V[ib1] : INFINITY};
+        const double c[2] = {V[ic0], V[ic1]};
+        if (!inner && (ia0 | ia1 | ib0 | ib1)) continue;  // one representative of the missed-box case
         // streaming reference
         prt::HitStack S;
         S.flags = 0;
@@ -160,44 +172,24 @@ long long prt_emul_selfcheck_left_deep(long long* cases_out) {
         double want2 = INFINITY; int wl2 = -1;
         { const int q = prt::buf_of(S, 0);
           for (int k = 0; k < S.len[0]; ++k) if (S.t[q][k] > 0) { want2 = S.t[q][k]; wl2 = S.leaf[q][k]; break; } }
+        const bool tie2 = tie;
         prt::merge_lists(S, 0, op2, ncn, [&](int j) { return c[j]; }, [&](int) { return 12; }, tie);
         double want3 = INFINITY; int wl3 = -1;
         { const int q = prt::buf_of(S, 0);
           for (int k = 0; k < S.len[0]; ++k) if (S.t[q][k] > 0) { want3 = S.t[q][k]; wl3 = S.leaf[q][k]; break; } }
-        // closed form, first merge only (shape 2)
-        bool keep[4]; int pos[4]; bool t2 = false;
-        prt::merge22(op1, a[0], a[1], b[0], b[1], keep, pos, t2);
-        double ct = INFINITY; int cl = -1;
-        prt::take_hit(keep[0], a[0], 10, ct, cl); prt::take_hit(keep[1], a[1], 10, ct, cl);
-        prt::take_hit(keep[2], b[0], 11, ct, cl); prt::take_hit(keep[3], b[1], 11, ct, cl);
         ++cases;
-        if (!(ct == want2 && cl == wl2) && op2 == 1 && ic0 == 0 && ic1 == 0) ++bad;
-        // closed form, both merges (shape 3), same code as eval_left_deep
-        const double x[4] = {a[0], a[1], b[0], b[1]};
-        unsigned km = 0;
-        for (int e = 0; e < 4; ++e) km |= keep[e] ? (1u << pos[e]) : 0u;
-        const bool vc0 = c[0] < INFINITY, vc1 = c[1] < INFINITY;
-        const int start = (op2 == PRT_DIFFERENCE) ? 1 : 0, sR = (op2 == PRT_DIFFERENCE) ? -1 : 1;
-        int lb0 = 0, lb1 = 0; bool keep2[4];
-        for (int e = 0; e < 4; ++e) {
-          const bool l0 = c[0] < x[e], l1 = c[1] < x[e];
-          const int rb = (int)l0 + (int)l1;
-          lb0 += (int)(keep[e] && !l0); lb1 += (int)(keep[e] && !l1);
-          const int idx = prt::popc32(km & ((1u << pos[e]) - 1u));
-          const int up = (idx & 1) ? -1 : 1;
-          const int cnt = start + ((idx + 1) & 1) + sR * (rb & 1);
-          keep2[e] = keep[e] && prt::csg_keep(op2, cnt, cnt - up);
+        // closed form, shape 2: (A op1 B), C absent
+        double ct; int cl; bool t2 = false;
+        if (op2 == 1 && ic0 == 0 && ic1 == 0) {
+          prt::left_deep_first_hit(tt2, a[0], a[1], b[0], b[1], INFINITY, INFINITY, 10, 11, -1, ct, cl, t2);
+          if (!(ct == want2 && cl == wl2) || (tie2 && !t2)) ++bad;
         }
-        int cnt = start + (lb0 & 1) + sR;
-        const bool kc0 = vc0 && prt::csg_keep(op2, cnt, cnt - sR);
-        cnt = start + (lb1 & 1);
-        const bool kc1 = vc1 && prt::csg_keep(op2, cnt, cnt + sR);
-        ct = INFINITY; cl = -1;
-        prt::take_hit(keep2[0], a[0], 10, ct, cl); prt::take_hit(keep2[1], a[1], 10, ct, cl);
-        prt::take_hit(keep2[2], b[0], 11, ct, cl); prt::take_hit(keep2[3], b[1], 11, ct, cl);
-        prt::take_hit(kc0, c[0], 12, ct, cl); prt::take_hit(kc1, c[1], 12, ct, cl);
-        if (!(ct == want3 && cl == wl3)) ++bad;
+        // closed form, shape 3
+        bool t3 = false;
+        prt::left_deep_first_hit(tt3, a[0], a[1], b[0], b[1], c[0], c[1], 10, 11, 12, ct, cl, t3);
+        if (!(ct == want3 && cl == wl3) || (tie && !t3)) ++bad;
       }
+    }
   *cases_out = cases;
   return bad;
 }

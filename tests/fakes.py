@@ -135,6 +135,30 @@ class WedgeOfRays(_RefSource):
     _kind, _attr = 13, "_angle"
 
 
+class Lamp:
+    """Stand-in for pyrayt.components.Lamp (:616-654): attributes only; its own generate_rays draws from
+    NumPy's global stream like the reference's."""
+
+    def __init__(self, width, length, max_angle=90.0, wavelength=0.633, world=None):
+        self._width, self._length, self._max_angle, self._wavelength = width, length, max_angle * np.pi / 180, wavelength
+        self._world_coordinate_transform = np.eye(4) if world is None else np.asarray(world, dtype=float)
+
+    def generate_rays(self, n):
+        uv = np.random.random_sample((2, n))
+        theta, phi = np.arccos(1 - uv[0] * (1 - np.cos(self._max_angle))), uv[1] * 2 * np.pi
+        rays = np.zeros((2, 4, n))
+        rays[0, 3] = 1
+        rays[0, 1] = self._width * (np.random.random_sample(n) - 0.5)
+        rays[0, 2] = self._length * (np.random.random_sample(n) - 0.5)
+        rays[1, 0], rays[1, 1], rays[1, 2] = np.cos(theta), np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi)
+        rays = np.matmul(self._world_coordinate_transform, rays)
+        rays[1] /= np.linalg.norm(rays[1], axis=0)
+        out = np.zeros((13, n))
+        out[:8] = rays.reshape(8, n)
+        out[9], out[10], out[11], out[12] = 100.0 * np.cos(theta), self._wavelength, 1.0, np.arange(n)
+        return out
+
+
 class OrthographicCamera:
     """Stand-in for tinygfx.g3d.OrthographicCamera (world_objects.py:499-537): rays along +x."""
 

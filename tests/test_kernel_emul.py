@@ -67,9 +67,10 @@ def test_both_traversals_of_the_nearest_hit_search(traversal, monkeypatch):
 
 
 def test_closed_form_left_deep_merge_equals_streaming_merge():
-    """All sorted pairs over {-inf,-2,-1,1,2,3,+inf} for A, B, C and all 9 operation pairs."""
+    """All sorted pairs over {-inf,-2,-1,1,2,3,+inf} for A, B, C and all 9 operation pairs, plus the
+    missed-inner-box case for every C."""
     bad, cases = emul.selfcheck_left_deep()
-    assert cases == 9 * 28 ** 3 and bad == 0
+    assert cases == 9 * (28 ** 3 + 28) and bad == 0
 
 
 def test_random_scene_stress():
