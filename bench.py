@@ -503,6 +503,10 @@ def run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, ma
     barrier()
     ms = max_over_ranks(t0.elapsed_time(t1)) / steps
     chk = float(h_frame[5, :1024].sum())  # touch the host result
+    # the host-side ceiling of this path on this box: plain pinned copies, every rank at the same time
+    from pyrayt_b200 import dist as pdist
+
+    peak = pdist.measure_host_copy_peak(d_rays.device, 2 << 30, world)
     lean = engine.last_transfer == "lean"  # what the timed steps used (chosen by the engine's own timing)
     out = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
            "h2d_bytes_per_step": int(h_rays.numel() * 8),
@@ -516,6 +520,12 @@ def run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, ma
                                                    "the engine timed both)")),
            "transfer_ms_per_step_measured": {k: v * rows for k, v in engine._xfer_ms_per_row.items()},
            "host_checksum": chk}
+    moved = out["d2h_bytes_per_step"] + out["h2d_bytes_per_step"]  # per rank; copies are serial within a rank
+    floor_ms = (out["d2h_bytes_per_step"] / peak["d2h_gbs_per_rank"] + out["h2d_bytes_per_step"] / peak["h2d_gbs_per_rank"]) / 1e6
+    out["host_peak"] = dict(peak, what="measured in this run: pinned D2H / H2D copy rate with all ranks copying at once")
+    out["host_floor_ms_per_step"] = floor_ms  # the bytes this path moves, at the measured copy rates, nothing else
+    out["frac_of_host_peak"] = floor_ms / ms
+    out["bus_bytes_per_step"] = int(moved)
     del h_frame
 
     # the same call chain when the user reads per-field spot statistics instead of the whole frame:

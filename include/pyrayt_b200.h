@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PRT_ABI_VERSION 2
+#define PRT_ABI_VERSION 3
 
 /* rows of the reference RaySet, (13, N) float64 row-major (pyrayt/_pyrayt.py:13-144) */
 #define PRT_RAY_ROWS 13
@@ -125,11 +125,23 @@ typedef enum prt_record_mode {
 typedef struct prt_params {
   int32_t generation_limit; /* RayTracer generation_limit (pyrayt/_pyrayt.py:212,:444)  */
   int32_t record_mode;      /* prt_record_mode                                          */
-  int32_t flags;            /* reserved, 0                                              */
+  int32_t flags;            /* PRT_FLAG_* bits, 0 = the plain FP64 trace                */
   int32_t reserved;
   double ray_offset;        /* RayTracer.ray_offset_value = 1e-6 (pyrayt/_pyrayt.py:190)*/
   int64_t detector_sid;     /* for PRT_RECORD_SURFACE                                   */
 } prt_params;
+
+/*
+ * prt_params.flags
+ * PRT_FLAG_DIAGNOSE: besides tracing, count the rays the north star excludes from the bit-exact id
+ * contract -- rays "within 1e-9 of grazing or CSG seams".  Operational definition: in some generation the
+ * nearest-hit search (_st_propagate, pyrayt/_pyrayt.py:370-392) answers differently when the ray's origin is
+ * displaced by 1e-9 x max(1, |origin|_inf) perpendicular to its direction (four displacements: +-e1, +-e2,
+ * e1 = unit(v x axis of the smallest |v_k|), e2 = (v x e1) / |v|).  A hit that turns into a miss or a
+ * miss that turns into a hit counts the ray in grazing_rays, a hit on a different surface in seam_rays.
+ * Five nearest-hit searches per generation instead of one: a diagnostic, not the timed path.
+ */
+#define PRT_FLAG_DIAGNOSE 1
 
 /* device-resident counters, zeroed by the caller before prt_trace */
 typedef struct prt_counters {
@@ -145,7 +157,9 @@ typedef struct prt_counters {
   uint64_t limit_rays;         /* rays stopped by generation_limit                                     */
   uint64_t absorber_segments;  /* segments that ended on an absorber                                   */
   uint64_t mirror_segments;    /* segments that ended on a mirror (the rest are glass)                 */
-  uint64_t reserved[4];
+  uint64_t grazing_rays;       /* PRT_FLAG_DIAGNOSE: rays with a generation whose hit <-> miss flips under a 1e-9 shift */
+  uint64_t seam_rays;          /* PRT_FLAG_DIAGNOSE: rays with a generation whose hit surface changes under a 1e-9 shift */
+  uint64_t reserved[2];
 } prt_counters;
 
 /*

@@ -36,6 +36,11 @@ def lib():
             ctypes.c_void_p, _dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_int,
             _dp, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64),
         ]
+        _LIB.prt_oracle_trace_diagnose.restype = ctypes.c_int64
+        _LIB.prt_oracle_trace_diagnose.argtypes = [
+            ctypes.c_void_p, _dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+            ctypes.POINTER(ctypes.c_uint64),
+        ]
         _LIB.prt_oracle_intersect.restype = ctypes.c_int
         _LIB.prt_oracle_intersect.argtypes = [
             ctypes.c_void_p, ctypes.c_int, _dp, ctypes.c_int64, _dp, ctypes.POINTER(ctypes.c_int64),
@@ -81,6 +86,20 @@ def trace(scene, rays: np.ndarray, generation_limit: int = 10, ray_offset: float
                                _p(frame), frame.shape[1], ctr)
     assert rows2 == rows
     return frame[:, :rows], counters
+
+
+def diagnose(scene, rays: np.ndarray, generation_limit: int = 10, ray_offset: float = 1e-6, threads: int = 1):
+    """The PRT_FLAG_DIAGNOSE counters (include/pyrayt_b200.h): the trace's counters plus ``grazing_rays`` and
+    ``seam_rays`` -- rays whose nearest-hit answer changes when the origin moves by 1e-9."""
+    rays = np.ascontiguousarray(rays, dtype=np.float64)
+    n = rays.shape[1]
+    desc = scene.as_desc()
+    ctr = (ctypes.c_uint64 * 8)()
+    rows = lib().prt_oracle_trace_diagnose(ctypes.byref(desc), _p(rays), n, n, generation_limit, ray_offset, threads,
+                                           ctr)
+    if rows < 0:
+        raise RuntimeError(f"oracle trace failed: {rows}")
+    return dict(zip(COUNTER_NAMES + ("grazing_rays", "seam_rays"), [int(x) for x in ctr]))
 
 
 def trace_timed(scene, rays: np.ndarray, generation_limit: int, ray_offset: float, threads: int, frame: np.ndarray):

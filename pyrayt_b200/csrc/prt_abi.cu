@@ -16,7 +16,7 @@
 
 
 extern "C" {
-cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, cudaStream_t st);
+cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, int diagnose, cudaStream_t st);
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
                             long long* gen_offsets, cudaStream_t st);
 cudaError_t prt_launch_gather(const prt::GatherArgs* a, int layout, cudaStream_t st);
@@ -191,7 +191,8 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
   a.n_rays = n_rays;
   a.stride = ray_stride;
   a.ctr = d_counters;
-  cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, scene->generic, (cudaStream_t)cuda_stream);
+  cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, scene->generic, (p->flags & PRT_FLAG_DIAGNOSE) ? 1 : 0,
+                                   (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "trace kernel launch");
   return PRT_OK;
 }

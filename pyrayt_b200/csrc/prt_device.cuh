@@ -996,7 +996,43 @@ struct StepCounters {
   unsigned w0, w1;
 };
 constexpr unsigned kCtrTie = 1u << 16, kCtrUntr = 1u << 17, kCtrNan = 1u << 18, kCtrLim = 1u << 19,
-                   kCtrAbs = 1u << 20;
+                   kCtrAbs = 1u << 20, kCtrGraze = 1u << 21, kCtrSeam = 1u << 22;
+
+// PRT_FLAG_DIAGNOSE (include/pyrayt_b200.h): does the nearest-hit search answer differently when the origin
+// is displaced by 1e-9 x max(1, |p|_inf) perpendicular to the direction?  Returns kCtrGraze (hit <-> miss)
+// and / or kCtrSeam (another surface).  Plain IEEE arithmetic in this order (oracle/trace_oracle.c restates it).
+template <bool GENERIC>
+PRT_HD unsigned diagnose_generation(const SceneView& sc, double p0, double p1, double p2, double v0, double v1,
+                                    double v2, double vn, int skip, HitStack* S, int hit_leaf) {
+  const double a0 = fabs(v0), a1 = fabs(v1), a2 = fabs(v2);
+  const int k = (a0 <= a1) ? ((a0 <= a2) ? 0 : 2) : ((a1 <= a2) ? 1 : 2);
+  // e1 = v x axis_k
+  double e0 = (k == 0) ? 0.0 : ((k == 1) ? -v2 : v1);
+  double e1 = (k == 0) ? v2 : ((k == 1) ? 0.0 : -v0);
+  double e2 = (k == 0) ? -v1 : ((k == 1) ? v0 : 0.0);
+  const double en = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+  e0 = e0 / en;
+  e1 = e1 / en;
+  e2 = e2 / en;
+  // e2 = (v x e1) / |v|
+  const double f0 = (v1 * e2 - v2 * e1) / vn, f1 = (v2 * e0 - v0 * e2) / vn, f2 = (v0 * e1 - v1 * e0) / vn;
+  const double delta = 1e-9 * fmax(1.0, fmax(fabs(p0), fmax(fabs(p1), fabs(p2))));
+  unsigned out = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int q = 0; q < 4; ++q) {
+    const double s = (q & 1) ? -delta : delta;
+    const double d0 = (q < 2) ? e0 : f0, d1 = (q < 2) ? e1 : f1, d2 = (q < 2) ? e2 : f2;
+    double t;
+    int leaf;
+    bool tie = false;
+    nearest_hit<GENERIC>(sc, p0 + s * d0, p1 + s * d1, p2 + s * d2, v0, v1, v2, skip, S, t, leaf, tie);
+    if (leaf != hit_leaf) out |= ((leaf < 0) | (hit_leaf < 0)) ? kCtrGraze : kCtrSeam;
+  }
+  return out;
+}
+
 
 // A ray that leaves a convex solid through one of its faces (its new direction has a clearly positive
 // component along the outward normal there) cannot hit that solid again until it changes direction:

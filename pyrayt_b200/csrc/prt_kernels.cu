@@ -37,7 +37,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #define PRT_MIN_BLOCKS 2
 #endif
 
-template <bool RECORD, bool GENERIC>
+template <bool RECORD, bool GENERIC, bool DIAG = false>
 __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char s_blob[];
   __shared__ int s_wcount[kTileRays / 32];
@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
         bool tie = false;
         nearest_hit<GENERIC>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, rs.skip, S, hit_t, hit_leaf, tie);
         if (tie) ctr.w1 |= kCtrTie;
+        if (DIAG)  // PRT_FLAG_DIAGNOSE: four more searches from origins displaced by 1e-9
+          ctr.w1 |= diagnose_generation<GENERIC>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, vn, rs.skip, S,
+                                                 hit_leaf);
       }
       s_ctr0[threadIdx.x] = ctr.w0;
       s_ctr1[threadIdx.x] = ctr.w1;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
 
   // counters: warp-reduce, one atomic per warp and counter
   const StepCounters sc_ctr = {s_ctr0[threadIdx.x], s_ctr1[threadIdx.x]};
-  unsigned long long vals[11] = {valid ? 1ull : 0ull,
+  unsigned long long vals[13] = {valid ? 1ull : 0ull,
                                  sc_ctr.w0 & 0xffffu,
                                  sc_ctr.w0 >> 16,
                                  c_drop,
@@ -187,8 +190,10 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
                                  (sc_ctr.w1 & kCtrNan) ? 1ull : 0ull,
                                  (sc_ctr.w1 & kCtrLim) ? 1ull : 0ull,
                                  (sc_ctr.w1 & kCtrAbs) ? 1ull : 0ull,
-                                 sc_ctr.w1 & 0xffffu};
-  unsigned long long* dst[11] = {
+                                 sc_ctr.w1 & 0xffffu,
+                                 (sc_ctr.w1 & kCtrGraze) ? 1ull : 0ull,
+                                 (sc_ctr.w1 & kCtrSeam) ? 1ull : 0ull};
+  unsigned long long* dst[13] = {
       reinterpret_cast<unsigned long long*>(&a.ctr->rays),
       reinterpret_cast<unsigned long long*>(&a.ctr->generations),
       reinterpret_cast<unsigned long long*>(&a.ctr->segments),
@@ -199,9 +204,11 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
       reinterpret_cast<unsigned long long*>(&a.ctr->nan_rays),
       reinterpret_cast<unsigned long long*>(&a.ctr->limit_rays),
       reinterpret_cast<unsigned long long*>(&a.ctr->absorber_segments),
-      reinterpret_cast<unsigned long long*>(&a.ctr->mirror_segments)};
+      reinterpret_cast<unsigned long long*>(&a.ctr->mirror_segments),
+      reinterpret_cast<unsigned long long*>(&a.ctr->grazing_rays),
+      reinterpret_cast<unsigned long long*>(&a.ctr->seam_rays)};
 #pragma unroll
-  for (int q = 0; q < 11; ++q) {
+  for (int q = 0; q < (DIAG ? 13 : 11); ++q) {
     const unsigned long long s = warp_sum(vals[q]);
     if (lane == 0 && s) atomicAdd(dst[q], s);
   }
@@ -638,21 +645,26 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters,
 
 // ---------------------------------------------------------------- launchers used by prt_abi.cpp
 
-template <bool RECORD, bool GENERIC>
+template <bool RECORD, bool GENERIC, bool DIAG = false>
 static cudaError_t launch_trace_variant(const prt::TraceArgs* a, unsigned tiles, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(prt::trace_kernel<RECORD, GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  prt::trace_kernel<RECORD, GENERIC><<<tiles, prt::kTileRays, smem, st>>>(*a);
+    cudaFuncSetAttribute(prt::trace_kernel<RECORD, GENERIC, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+  prt::trace_kernel<RECORD, GENERIC, DIAG><<<tiles, prt::kTileRays, smem, st>>>(*a);
   return cudaGetLastError();
 }
 
 extern "C" {
 
-// generic != 0: some component needs the interpreter for arbitrary CSG trees
-cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, cudaStream_t st) {
+// generic != 0: some component needs the interpreter for arbitrary CSG trees; diagnose != 0: PRT_FLAG_DIAGNOSE
+// (one variant, the one with the interpreter, serves every scene)
+cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, int diagnose, cudaStream_t st) {
   const long long tiles = (a->n_rays + prt::kTileRays - 1) / prt::kTileRays;
   if (tiles == 0) return cudaSuccess;
   const size_t smem = (size_t)a->blob_bytes;
+  if (diagnose)
+    return record ? launch_trace_variant<true, true, true>(a, (unsigned)tiles, smem, st)
+                  : launch_trace_variant<false, true, true>(a, (unsigned)tiles, smem, st);
   if (record) {
     return generic ? launch_trace_variant<true, true>(a, (unsigned)tiles, smem, st)
                    : launch_trace_variant<true, false>(a, (unsigned)tiles, smem, st);

@@ -145,3 +145,45 @@ def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
         return node
     except (OSError, ValueError, AttributeError, RuntimeError):
         return None
+
+
+def measure_host_copy_peak(device, nbytes: int = 4 << 30, world: int = 1, repeats: int = 3) -> dict:
+    """The host-side ceiling of the end-to-end path: pinned device -> host copy rate with every rank
+    copying at the same time (plain cudaMemcpyAsync through ``Tensor.copy_``), and the host -> device
+    rate the same way.  Timed on the device (CUDA events), max over ranks.  Returns GB/s per rank and
+    in aggregate; with a process group the start is aligned by a barrier."""
+    import torch
+    import torch.distributed as dist
+
+    multi = world > 1 and dist.is_available() and dist.is_initialized()
+    n = max(1, nbytes // 8)
+    d = torch.empty(n, dtype=torch.float64, device=device)
+    d.fill_(1.0)
+    h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    h.fill_(0.0)  # first touch: the pages exist before anything is timed
+
+    def timed(dst, src):
+        best = float("inf")
+        for _ in range(repeats):
+            if multi:
+                dist.barrier()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if multi:
+                t = torch.tensor([ms], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            best = min(best, ms)
+        return best
+
+    d2h_ms = timed(h, d)
+    h2d_ms = timed(d, h)
+    gb = n * 8 / 1e9
+    return {"d2h_gbs_per_rank": gb / (d2h_ms * 1e-3), "d2h_gbs_aggregate": world * gb / (d2h_ms * 1e-3),
+            "h2d_gbs_per_rank": gb / (h2d_ms * 1e-3), "h2d_gbs_aggregate": world * gb / (h2d_ms * 1e-3),
+            "bytes_per_rank": n * 8, "how": "pinned cudaMemcpyAsync, all ranks at once, best of %d, max over ranks" % repeats}

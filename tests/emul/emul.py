@@ -25,15 +25,16 @@ def lib():
     return _LIB
 
 
-def trace(scene, rays, generation_limit, ray_offset=1e-6):
-    """Returns (frame (15, rows) ordered (generation, input order), counters)."""
+def trace(scene, rays, generation_limit, ray_offset=1e-6, diagnose=False):
+    """Returns (frame (15, rows) ordered (generation, input order), counters); diagnose = PRT_FLAG_DIAGNOSE."""
     rays = np.ascontiguousarray(rays, dtype=np.float64)
     n = rays.shape[1]
     cap = max(1, n * generation_limit)
     rows = np.empty((cap, 15))
     nrows = np.zeros(max(n, 1), dtype=np.int32)
-    ctr = (ctypes.c_ulonglong * 8)()
+    ctr = (ctypes.c_ulonglong * 10)()
     desc = scene.as_desc()
+    lib().prt_emul_set_diagnose(ctypes.c_int(1 if diagnose else 0))
     total = lib().prt_emul_trace(ctypes.byref(desc), rays.ctypes.data_as(_dp), ctypes.c_longlong(n),
                                  ctypes.c_longlong(n), ctypes.c_int(generation_limit), ctypes.c_double(ray_offset),
                                  rows.ctypes.data_as(_dp), ctypes.c_longlong(cap),
@@ -43,8 +44,10 @@ def trace(scene, rays, generation_limit, ray_offset=1e-6):
     # ray-major -> (generation round, input order)
     rnd = np.concatenate([np.arange(k) for k in nrows[:n]]) if total else np.zeros(0, dtype=np.int64)
     order = np.argsort(rnd, kind="stable")
-    names = ("rays", "generations", "segments", "tie_rays", "untraceable_hits", "nan_rays", "limit_rays")
-    return rows[order].T.copy(), dict(zip(names, [int(x) for x in ctr[:7]]))
+    lib().prt_emul_set_diagnose(ctypes.c_int(0))
+    names = ("rays", "generations", "segments", "tie_rays", "untraceable_hits", "nan_rays", "limit_rays",
+             "grazing_rays", "seam_rays")
+    return rows[order].T.copy(), dict(zip(names, [int(x) for x in ctr[:9]]))
 
 
 def intersect(scene, component, rays):

@@ -17,7 +17,12 @@ using std::isnan;
 #include "../../pyrayt_b200/csrc/prt_literal.cuh"
 #include "../../pyrayt_b200/csrc/prt_encode.h"
 
+static int g_diagnose = 0;
+
 extern "C" {
+
+// PRT_FLAG_DIAGNOSE for the following prt_emul_trace calls (counters[7] = grazing rays, [8] = seam rays)
+void prt_emul_set_diagnose(int on) { g_diagnose = on; }
 
 // frame: row-major scratch (rows ray-major, 15 per row) up to cap rows; nrows[i] rows per ray.
 // returns total rows or <0.
@@ -37,7 +42,7 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   const prt::SceneView sc = prt::make_view(blob.data());
   long long total = 0;
   prt::StepCounters c = {0, 0};
-  unsigned long long tie_rays = 0, gens = 0, segs = 0, untr = 0, nans = 0, lims = 0;
+  unsigned long long tie_rays = 0, gens = 0, segs = 0, untr = 0, nans = 0, lims = 0, graze = 0, seam = 0;
   for (long long i = 0; i < n; ++i) {
     prt::RayState r;
     r.skip = -1;
@@ -51,6 +56,16 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
     c.w1 &= ~prt::kCtrTie;
     for (int g = 0; g < generation_limit; ++g) {
       prt::StepOut o;
+      if (g_diagnose) {  // as trace_kernel<.., DIAG = true>: the nearest hit, then four displaced searches
+        const double vn = std::sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
+        if (!prt::isz(vn) && !(std::isnan(r.v0) || std::isnan(r.v1) || std::isnan(r.v2))) {
+          double bt;
+          int bl;
+          bool tie = false;
+          prt::nearest_hit<true>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, r.skip, &S, bt, bl, tie);
+          c.w1 |= prt::diagnose_generation<true>(sc, r.p0, r.p1, r.p2, r.v0, r.v1, r.v2, vn, r.skip, &S, bl);
+        }
+      }
       const bool on = prt::trace_step<true>(sc, r, g, generation_limit, &S, o, c);
       if (o.row) {
         if (total < cap) {
@@ -71,6 +86,8 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
     untr += (c.w1 & prt::kCtrUntr) ? 1 : 0;
     nans += (c.w1 & prt::kCtrNan) ? 1 : 0;
     lims += (c.w1 & prt::kCtrLim) ? 1 : 0;
+    graze += (c.w1 & prt::kCtrGraze) ? 1 : 0;
+    seam += (c.w1 & prt::kCtrSeam) ? 1 : 0;
     c.w0 = 0;
     c.w1 = 0;
     nrows[i] = k;
@@ -82,6 +99,8 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   counters[4] = untr;
   counters[5] = nans;
   counters[6] = lims;
+  counters[7] = graze;
+  counters[8] = seam;
   return total;
 }
 
