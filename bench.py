@@ -38,6 +38,7 @@ CPU_SAMPLE_RAYS = 1 << 18          # oracle port (C restatement), all host threa
 NUMPY_SAMPLE_RAYS_1CORE = 1 << 14  # unmodified NumPy reference as a user runs it (one core), ~10 s
 NUMPY_SAMPLE_RAYS_PER_PROC = 1 << 12  # reference arm: rays per worker process and step
 MISMATCH_SAMPLE_RAYS = 1 << 12     # stable-vs-default argsort report
+DIAGNOSE_SAMPLE_RAYS = 1 << 22     # grazing / seam ray count (PRT_FLAG_DIAGNOSE), untimed
 
 
 def parse_args():
@@ -372,6 +373,17 @@ def main():
     rows_total = int(sum_over_ranks(rows))
     k1 = sum(k1_ms) / len(k1_ms)
 
+    # ------------------------------------------------------------------ rays excluded from the id contract
+    # (north star: "rays within 1e-9 of grazing or CSG seams ... are counted and reported"): one untimed
+    # PRT_FLAG_DIAGNOSE trace of the first DIAGNOSE_SAMPLE_RAYS rays of this rank (5 searches per generation)
+    nd = min(n, DIAGNOSE_SAMPLE_RAYS)
+    dres = engine.trace(d_rays[:, :nd], generation_limit=G, record="none", diagnose=True)
+    near = {"rays": nd, "grazing_rays": dres.counters["grazing_rays"], "seam_rays": dres.counters["seam_rays"],
+            "tie_rays": dres.counters["tie_rays"],
+            "what": "PRT_FLAG_DIAGNOSE on this rank's first rays: rays for which the nearest-hit answer of some "
+                    "generation changes (hit <-> miss: grazing; other surface: seam) when the origin is displaced "
+                    "by 1e-9 x max(1, |origin|) perpendicular to the direction; tie_rays: equal finite CSG keys"}
+
     # ------------------------------------------------------------------ roofline of the trace kernel
     hbm_peak, peak_src = measured_peaks()
     abytes = roofline.algorithmic_bytes(n, rows)
@@ -462,7 +474,7 @@ def main():
             "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e, "readout": readout,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "counters": {k: counters[k] for k in ("rays", "generations", "segments", "tie_rays", "rows_dropped")},
-            "argsort_mismatch": mismatch,
+            "argsort_mismatch": mismatch, "near_degenerate": near,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

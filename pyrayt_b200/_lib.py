@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYRAYT_B200_LIB") or os.path.join(_HERE, "libpyrayt_b200.so")  # override: experiments only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FRAME_COLS = 15
 STAGE_COLS = 9  # doubles per staged record (PRT_STAGE_COLS)
 RAY_ROWS = 13
@@ -28,7 +28,9 @@ FRAME_COLUMNS = (
 COUNTER_FIELDS = (
     "rays", "generations", "segments", "rows_reserved", "rows_dropped", "tie_rays",
     "untraceable_hits", "bad_w", "nan_rays", "limit_rays", "absorber_segments", "mirror_segments",
+    "grazing_rays", "seam_rays",  # PRT_FLAG_DIAGNOSE only
 )
+FLAG_DIAGNOSE = 1  # PRT_FLAG_DIAGNOSE
 COUNTER_WORDS = 16
 
 # every symbol include/pyrayt_b200.h declares

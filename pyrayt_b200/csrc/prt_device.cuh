@@ -1000,7 +1000,7 @@ constexpr unsigned kCtrTie = 1u << 16, kCtrUntr = 1u << 17, kCtrNan = 1u << 18, 
 
 // PRT_FLAG_DIAGNOSE (include/pyrayt_b200.h): does the nearest-hit search answer differently when the origin
 // is displaced by 1e-9 x max(1, |p|_inf) perpendicular to the direction?  Returns kCtrGraze (hit <-> miss)
-// and / or kCtrSeam (another surface).  Plain IEEE arithmetic in this order (oracle/trace_oracle.c restates it).
+// and / or kCtrSeam (another surface).  Plain IEEE arithmetic in this order (the CPU checker restates it).
 template <bool GENERIC>
 PRT_HD unsigned diagnose_generation(const SceneView& sc, double p0, double p1, double p2, double v0, double v1,
                                     double v2, double vn, int skip, HitStack* S, int hit_leaf) {

@@ -99,8 +99,12 @@ class Engine:
     def trace(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
               detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
               host_frame=None, zero_copy: bool = False, k1_events=None, method: str = "auto", host_rays=None,
-              lean="auto") -> TraceResult:
+              lean="auto", diagnose: bool = False) -> TraceResult:
         """Trace a device RaySet.
+
+        diagnose: PRT_FLAG_DIAGNOSE -- also count the rays "within 1e-9 of grazing or CSG seams" (counters
+        ``grazing_rays`` / ``seam_rays``: the nearest-hit answer of some generation changes when the origin is
+        displaced by 1e-9; include/pyrayt_b200.h).  Five searches per generation: a diagnostic, not the fast path.
 
         method: "single" = one kernel for all generations + ordering pass (staging buffer and frame: 240 B
         of device memory per row); "wavefront" = one launch per generation writing rows in place
@@ -124,7 +128,8 @@ class Engine:
         mode = _RECORD_MODES[record]
         if method not in ("auto", "single", "wavefront"):
             raise ValueError("method must be 'auto', 'single' or 'wavefront'")
-        if mode != _lib.RECORD_NONE and not zero_copy and k1_events is None and method != "single":
+        flags = _lib.FLAG_DIAGNOSE if diagnose else 0
+        if mode != _lib.RECORD_NONE and not zero_copy and k1_events is None and method != "single" and not diagnose:
             rows_guess = capacity if capacity is not None else min(n * G, n * self.rows_per_ray_hint * 1.05)
             total = torch.cuda.get_device_properties(self.device).total_memory
             if method == "wavefront" or 8 * (_lib.STAGE_COLS + _lib.FRAME_COLS) * rows_guess > 0.8 * total:
@@ -135,7 +140,7 @@ class Engine:
         launches = 0
         with torch.cuda.device(self.device):
             ctr = self._buf("ctr", _lib.COUNTER_WORDS, torch.int64)
-            params = _lib.PrtParams(G, mode, 0, 0, float(ray_offset), int(detector_sid))
+            params = _lib.PrtParams(G, mode, flags, 0, float(ray_offset), int(detector_sid))
             if mode == _lib.RECORD_NONE:
                 ctr.zero_()
                 _lib.check(self.lib.prt_trace(self._handle, ctypes.byref(params), d_rays.data_ptr(), n, stride,

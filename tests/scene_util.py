@@ -221,3 +221,19 @@ def random_scene_and_rays(seed, n_rays=512):
     rays = make_rays(o, d)
     rays[10] = rng.uniform(0.45, 0.7, n_rays)
     return build(comps), rays
+
+
+def grazing_and_seam_case():
+    """A unit mirror sphere and two absorber planes that share the edge y = 0 at x = 5, with rays aimed
+    2e-10 inside / outside the sphere's silhouette, through the plane seam, at the outer plane edge, and
+    well away from all of them.  Returns (scene, rays, expected (grazing, seam) flags per ray)."""
+    sph = Leaf(SPHERE, [1.0], mat=MAT_MIRROR)
+    pl_a = Leaf(PLANE, [2.0, 2.0], world=translate(5, 1.0, 0) @ rot_y(90))
+    pl_b = Leaf(PLANE, [2.0, 2.0], world=translate(5, -1.0, 0) @ rot_y(90))
+    scene = build([sph, pl_a, pl_b])
+    o = [[-3, 1 - 2e-10, 0], [-3, 1 + 2e-10, 0], [-3, 0.5, 0], [3, 3e-10, 0.2], [3, 0.3, 0.2], [3, 2.0 - 1e-10, 0.1]]
+    rays = make_rays(o, [[1, 0, 0]] * 6)
+    # ray 0 / 1: sphere <-> the plane behind it (a change of surface), ray 3: plane a <-> plane b,
+    # ray 5: plane a <-> nothing
+    expected = [(0, 1), (0, 1), (0, 0), (0, 1), (0, 0), (1, 0)]
+    return scene, rays, expected

@@ -34,6 +34,34 @@ def test_golden_case_matches_reference_and_oracle(name, cuda_device):
     assert res.counters["rows_dropped"] == 0 and res.counters["bad_w"] == 0
 
 
+def test_diagnose_counters_match_the_oracle(cuda_device):
+    """PRT_FLAG_DIAGNOSE: grazing / seam rays counted by the kernel == the oracle's, ray by ray on the crafted
+    case, in total on golden cases; the frame of a diagnosing trace is the ordinary frame."""
+    import torch
+
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+
+    scene, rays, expected = su.grazing_and_seam_case()
+    eng = pyrayt_b200.Engine(scene, device=0)
+    for i, (gz, sm) in enumerate(expected):
+        one = np.ascontiguousarray(rays[:, i:i + 1])
+        res = eng.trace(torch.from_numpy(one).cuda(), generation_limit=4, diagnose=True)
+        assert (res.counters["grazing_rays"], res.counters["seam_rays"]) == (gz, sm), i
+    res = eng.trace(torch.from_numpy(rays).cuda(), generation_limit=4, diagnose=True, record="none")
+    assert (res.counters["grazing_rays"], res.counters["seam_rays"]) == (1, 3)
+    for name in ("config4_stack", "config5_cavity", "nested_csg", "stop_ties"):
+        scene, rays, _, gl = load_case(name)
+        eng, res = _trace(scene, rays, gl, diagnose=True, to_host=True)
+        want, _ = oracle.trace(scene, rays, gl)
+        o = oracle.diagnose(scene, rays, gl)
+        assert np.array_equal(res.frame.numpy(), want, equal_nan=True), name
+        assert (res.counters["grazing_rays"], res.counters["seam_rays"]) == (o["grazing_rays"], o["seam_rays"]), name
+        plain = eng.trace(torch.from_numpy(np.ascontiguousarray(rays)).cuda(), generation_limit=gl)
+        assert plain.counters["grazing_rays"] == 0 and plain.counters["seam_rays"] == 0
+
+
 def test_edge_inputs(cuda_device):
     """Empty input, one ray, generation_limit 1, ray counts around the tile size, dead-on-arrival rays."""
     import torch

@@ -116,3 +116,21 @@ def test_equal_distances_go_to_the_earlier_component_in_any_visiting_order():
         assert np.array_equal(got, want, equal_nan=True)
         ends = want[5][want[0] == want[0].max()]
         assert first in set(want[5]) and second not in set(want[5]), (first, second, ends)
+
+
+def test_diagnose_counters_equal_the_oracle():
+    """PRT_FLAG_DIAGNOSE (rays within 1e-9 of grazing or CSG seams, counted by displacing the origin): the
+    kernel's per-ray code and the oracle agree ray by ray on a crafted case and in total on random scenes."""
+    scene, rays, expected = su.grazing_and_seam_case()
+    for i, (gz, sm) in enumerate(expected):
+        one = np.ascontiguousarray(rays[:, i:i + 1])
+        o = oracle.diagnose(scene, one, 4)
+        _, e = emul.trace(scene, one, 4, diagnose=True)
+        assert (o["grazing_rays"], o["seam_rays"]) == (gz, sm), i
+        assert (e["grazing_rays"], e["seam_rays"]) == (gz, sm), i
+    for seed in range(3000, 3012):
+        scene, rays = su.random_scene_and_rays(seed, n_rays=256)
+        o = oracle.diagnose(scene, rays, 12)
+        _, e = emul.trace(scene, rays, 12, diagnose=True)
+        assert (o["grazing_rays"], o["seam_rays"]) == (e["grazing_rays"], e["seam_rays"]), seed
+        assert o["generations"] == e["generations"]
