@@ -38,6 +38,7 @@ CPU_SAMPLE_RAYS = 1 << 18          # oracle port (C restatement), all host threa
 NUMPY_SAMPLE_RAYS_1CORE = 1 << 14  # unmodified NumPy reference as a user runs it (one core), ~10 s
 NUMPY_SAMPLE_RAYS_PER_PROC = 1 << 12  # reference arm: rays per worker process and step
 MISMATCH_SAMPLE_RAYS = 1 << 12     # stable-vs-default argsort report
+FP32_COMPARE_RAYS = 1 << 22        # FP32 fast mode vs FP64 frame agreement, untimed
 DIAGNOSE_SAMPLE_RAYS = 1 << 22     # grazing / seam ray count (PRT_FLAG_DIAGNOSE), untimed
 
 
@@ -53,6 +54,7 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-numpy", action="store_true", help="skip the NumPy-reference legs even if baseline/_ref exists")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the FP32 fast-mode leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--zero-copy", action="store_true", help="e2e: gather kernel writes straight into pinned host memory")
     ap.add_argument("--full-copy", action="store_true",
@@ -436,6 +438,11 @@ def main():
     e2e = None
     res = None  # drop the device frame of the last resident step before the host-buffer run
     torch.cuda.empty_cache()
+    # ------------------------------------------------------------------ the optional FP32 fast mode (north star)
+    fp32 = None
+    if not args.no_fp32 and not scene_needs_interpreter(scene):
+        fp32 = run_fp32_mode(torch, engine, d_rays, n, n_total, G, args.steps, ev, barrier, max_over_ranks)
+        torch.cuda.empty_cache()
     if not args.no_e2e:
         e2e = run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, max_over_ranks)
 
@@ -474,11 +481,62 @@ def main():
             "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "e2e": e2e, "readout": readout,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "counters": {k: counters[k] for k in ("rays", "generations", "segments", "tie_rays", "rows_dropped")},
-            "argsort_mismatch": mismatch, "near_degenerate": near,
+            "argsort_mismatch": mismatch, "near_degenerate": near, "fp32_mode": fp32,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def scene_needs_interpreter(scene):
+    """True when some component is not a bare surface or a left-deep tree of <= 3 leaves (FP32 mode: unsupported)."""
+    import numpy as np
+
+    for c in range(scene.n_components):
+        kinds = scene.node_kind[scene.comp_node_begin[c]: scene.comp_node_begin[c + 1]]
+        n = len(kinds)
+        ok = (n == 1) or (n == 3 and list(kinds[:2]) == [0, 0]) or (n == 5 and list(kinds[:2]) == [0, 0] and kinds[3] == 0)
+        if not ok:
+            return True
+    return False
+
+
+def run_fp32_mode(torch, engine, d_rays, n, n_total, G, steps, ev, barrier, max_over_ranks):
+    """PRT_FLAG_FP32: the same step in single precision (device-resident, like `value`), and its agreement with
+    the FP64 frame on this rank's first FP32_COMPARE_RAYS rays."""
+    from pyrayt_b200 import compare
+
+    k1, res = [], None
+    for it in range(3 + steps):
+        res = None  # one frame at a time
+        e0, e1 = ev(), ev()
+        e0.record()
+        res = engine.trace(d_rays, generation_limit=G, record="all", precision="fp32", k1_events=(e0, e1))
+        torch.cuda.synchronize()
+        if it >= 3:
+            k1.append(e0.elapsed_time(e1))
+    rows32 = res.rows
+    res = None
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(steps):
+        res = None
+        res = engine.trace(d_rays, generation_limit=G, record="all", precision="fp32")
+    t1.record()
+    barrier()
+    ms = max_over_ranks(t0.elapsed_time(t1)) / steps
+    res = None
+    nc = min(n, FP32_COMPARE_RAYS)
+    sub = d_rays[:, :nc]
+    a = engine.trace(sub, generation_limit=G)
+    b = engine.trace(sub, generation_limit=G, precision="fp32")
+    rep = compare.frame_agreement(a.frame, b.frame, int(sub[12, 0].item()), nc)
+    return {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": sum(k1) / len(k1),
+            "dtype": "f32", "rows": rows32,
+            "contract": "positions within 1e-5 of the scene scale, unit tilt and index within 1e-5, ids equal, "
+                        "except rays passing within that distance of an edge (counted below)",
+            "agreement_with_fp64": rep}
 
 
 def run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, max_over_ranks):

@@ -142,6 +142,21 @@ typedef struct prt_params {
  * Five nearest-hit searches per generation instead of one: a diagnostic, not the timed path.
  */
 #define PRT_FLAG_DIAGNOSE 1
+/*
+ * PRT_FLAG_FP32: the optional fast mode of the north star.  The whole generation loop -- transforms,
+ * intersections, CSG merge, nearest hit, normals, Snell / Sellmeier -- runs in single precision with FMA
+ * contraction and fast division / square root; the frame keeps its fifteen float64 columns.  Contract: the
+ * frame agrees with the FP64 frame to 1e-5 of the scene scale (positions; 1e-5 absolute for the unit tilt
+ * and the refractive index), surface and generation ids agree except for rays passing within that distance
+ * of an edge or seam.  A ray cannot leave a surface by the reference's 1e-6 offset in single precision
+ * (ulp(100) = 7.6e-6): instead, roots of the leaf just hit that lie within 2e-4 x max(1, |origin|) of the
+ * origin are taken as the crossing just made.  Scenes must consist of bare surfaces and left-deep CSG trees
+ * of <= 3 leaves (every reference factory); others return PRT_ERR_UNSUPPORTED.  Staged records are 40 bytes
+ * (5 of the PRT_STAGE_COLS columns): pass PRT_LAYOUT_FP32_RECORDS in prt_gather_frame's layout.
+ * Not available in prt_trace_wavefront.
+ */
+#define PRT_FLAG_FP32 2
+#define PRT_LAYOUT_FP32_RECORDS 0x100
 
 /* device-resident counters, zeroed by the caller before prt_trace */
 typedef struct prt_counters {

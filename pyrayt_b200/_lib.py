@@ -31,6 +31,9 @@ COUNTER_FIELDS = (
     "grazing_rays", "seam_rays",  # PRT_FLAG_DIAGNOSE only
 )
 FLAG_DIAGNOSE = 1  # PRT_FLAG_DIAGNOSE
+FLAG_FP32 = 2  # PRT_FLAG_FP32: the optional single-precision fast mode
+LAYOUT_FP32_RECORDS = 0x100  # prt_gather_frame: the staged records were written by an FP32 trace
+STAGE_COLS_FP32 = 5
 COUNTER_WORDS = 16
 
 # every symbol include/pyrayt_b200.h declares

@@ -17,6 +17,9 @@
 
 extern "C" {
 cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, int diagnose, cudaStream_t st);
+cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int n_leaves, int n_components, cudaStream_t st);
+cudaError_t prt_launch_gather_f32(const prt::GatherArgs* a, cudaStream_t st);
+size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components);
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
                             long long* gen_offsets, cudaStream_t st);
 cudaError_t prt_launch_gather(const prt::GatherArgs* a, int layout, cudaStream_t st);
@@ -191,6 +194,18 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
   a.n_rays = n_rays;
   a.stride = ray_stride;
   a.ctr = d_counters;
+  if (p->flags & PRT_FLAG_FP32) {
+    if (scene->generic)
+      return fail(PRT_ERR_UNSUPPORTED, "the FP32 fast mode traces bare surfaces and left-deep CSG trees of up to three "
+                                       "leaves (everything the reference's factories build); this scene needs FP64");
+    if (p->flags & PRT_FLAG_DIAGNOSE) return fail(PRT_ERR_UNSUPPORTED, "PRT_FLAG_DIAGNOSE is an FP64 diagnostic");
+    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 100 * 1024)
+      return fail(PRT_ERR_LIMIT, "scene too large for the FP32 fast mode's shared-memory staging");
+    cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->n_leaves, scene->n_components,
+                                           (cudaStream_t)cuda_stream);
+    if (e32 != cudaSuccess) return cuda_fail(e32, "trace kernel launch (fp32)");
+    return PRT_OK;
+  }
   cudaError_t e = prt_launch_trace(&a, record ? 1 : 0, scene->generic, (p->flags & PRT_FLAG_DIAGNOSE) ? 1 : 0,
                                    (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "trace kernel launch");
@@ -264,7 +279,10 @@ int prt_gather_frame(prt_scene* scene, const prt_records* rec, const double* d_r
     return fail(PRT_ERR_INVALID, "null argument");
   if (!frame) return fail(PRT_ERR_INVALID, "null frame");
   if (n_rays < 0 || (n_rays > 0 && !d_rays) || ray_stride < n_rays) return fail(PRT_ERR_INVALID, "bad ray buffer");
+  const bool f32_records = (layout & PRT_LAYOUT_FP32_RECORDS) != 0;
+  layout &= ~PRT_LAYOUT_FP32_RECORDS;
   if (layout != 0 && layout != 1) return fail(PRT_ERR_INVALID, "bad layout");
+  if (f32_records && layout != 0) return fail(PRT_ERR_UNSUPPORTED, "FP32 records expand to the column-major frame only");
   if (frame_capacity < 0 || (layout == 0 && frame_stride < frame_capacity)) return fail(PRT_ERR_INVALID, "bad frame");
   if (rec->n_tiles > 0x7fffffffLL) return fail(PRT_ERR_LIMIT, "too many tiles");
   if (rec->n_tiles * (int64_t)prt::kTileRays < n_rays) return fail(PRT_ERR_INVALID, "records.n_tiles too small");
@@ -285,7 +303,8 @@ int prt_gather_frame(prt_scene* scene, const prt_records* rec, const double* d_r
   a.frame = frame;
   a.frame_stride = frame_stride;
   a.frame_capacity = frame_capacity;
-  cudaError_t e = prt_launch_gather(&a, layout, (cudaStream_t)cuda_stream);
+  cudaError_t e = f32_records ? prt_launch_gather_f32(&a, (cudaStream_t)cuda_stream)
+                              : prt_launch_gather(&a, layout, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "gather kernel launch");
   return PRT_OK;
 }

@@ -729,7 +729,8 @@ PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, d
 // nine operation pairs, with and without the inner bounding box: tests/test_kernel_emul.py.)
 
 // running best of one component: first positive kept entry in merged order
-PRT_HD void take_hit(bool keep, double t, int leaf, double& ct, int& cl) {
+template <class T>
+PRT_HD void take_hit(bool keep, T t, int leaf, T& ct, int& cl) {
   const bool take = keep & (t > 0) & (t < ct);
   ct = take ? t : ct;
   cl = take ? leaf : cl;
@@ -742,10 +743,13 @@ PRT_HD bool tt_changes(unsigned tt, unsigned before, unsigned own) {
 
 // (a0,a1), (b0,b1), (c0,c1): sorted hit pairs of leaves A, B, C (+inf = missing entry; LEFT2: c = +inf and
 // tt ignores C).  Returns the nearest positive kept entry (ct, cl) and whether equal keys were compared.
-PRT_HD void left_deep_first_hit(unsigned tt, double a0, double a1, double b0, double b1, double c0, double c1,
-                                int la, int lb, int lc, double& ct, int& cl, bool& tie) {
-  const bool va0 = a0 < PRT_INF, va1 = a1 < PRT_INF, vb0 = b0 < PRT_INF, vb1 = b1 < PRT_INF;
-  const bool vc0 = c0 < PRT_INF, vc1 = c1 < PRT_INF;
+// (T = double on the FP64 path, float in the FP32 fast mode.)
+template <class T>
+PRT_HD void left_deep_first_hit(unsigned tt, T a0, T a1, T b0, T b1, T c0, T c1, int la, int lb, int lc, T& ct,
+                                int& cl, bool& tie) {
+  const T kInf = (T)PRT_INF;
+  const bool va0 = a0 < kInf, va1 = a1 < kInf, vb0 = b0 < kInf, vb1 = b1 < kInf;
+  const bool vc0 = c0 < kInf, vc1 = c1 < kInf;
   // y < x for every pair of entries of different leaves (bitwise logic on purpose: no short-circuit branches)
   const bool b0a0 = b0 < a0, b1a0 = b1 < a0, b0a1 = b0 < a1, b1a1 = b1 < a1;
   const bool c0a0 = c0 < a0, c1a0 = c1 < a0, c0a1 = c0 < a1, c1a1 = c1 < a1;
@@ -769,7 +773,7 @@ PRT_HD void left_deep_first_hit(unsigned tt, double a0, double a1, double b0, do
   const bool kb1 = vb1 & tt_changes(tt, inA_b1 | 2u | (inC_b1 << 2), 2u);
   const bool kc0 = vc0 & tt_changes(tt, inA_c0 | (inB_c0 << 1), 4u);
   const bool kc1 = vc1 & tt_changes(tt, inA_c1 | (inB_c1 << 1) | 4u, 4u);
-  ct = PRT_INF;
+  ct = kInf;
   cl = -1;
   take_hit(ka0, a0, la, ct, cl);
   take_hit(ka1, a1, la, ct, cl);

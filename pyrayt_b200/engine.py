@@ -99,8 +99,12 @@ class Engine:
     def trace(self, d_rays, generation_limit: int = 10, ray_offset: float = 1e-6, record: str = "all",
               detector_sid: int = -1, capacity: Optional[int] = None, to_host: bool = False,
               host_frame=None, zero_copy: bool = False, k1_events=None, method: str = "auto", host_rays=None,
-              lean="auto", diagnose: bool = False) -> TraceResult:
+              lean="auto", diagnose: bool = False, precision: str = "fp64") -> TraceResult:
         """Trace a device RaySet.
+
+        precision: "fp64" (the reference's arithmetic, bit-exact against the oracle) or "fp32", the optional fast
+        mode (PRT_FLAG_FP32, include/pyrayt_b200.h): the generation loop in single precision, frame values
+        within 1e-5 of the scene scale of the FP64 frame; scenes of bare surfaces and left-deep CSG trees only.
 
         diagnose: PRT_FLAG_DIAGNOSE -- also count the rays "within 1e-9 of grazing or CSG seams" (counters
         ``grazing_rays`` / ``seam_rays``: the nearest-hit answer of some generation changes when the origin is
@@ -128,8 +132,12 @@ class Engine:
         mode = _RECORD_MODES[record]
         if method not in ("auto", "single", "wavefront"):
             raise ValueError("method must be 'auto', 'single' or 'wavefront'")
-        flags = _lib.FLAG_DIAGNOSE if diagnose else 0
-        if mode != _lib.RECORD_NONE and not zero_copy and k1_events is None and method != "single" and not diagnose:
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        fp32 = precision == "fp32"
+        flags = (_lib.FLAG_DIAGNOSE if diagnose else 0) | (_lib.FLAG_FP32 if fp32 else 0)
+        if (mode != _lib.RECORD_NONE and not zero_copy and k1_events is None and method != "single" and not diagnose
+                and not fp32):
             rows_guess = capacity if capacity is not None else min(n * G, n * self.rows_per_ray_hint * 1.05)
             total = torch.cuda.get_device_properties(self.device).total_memory
             if method == "wavefront" or 8 * (_lib.STAGE_COLS + _lib.FRAME_COLS) * rows_guess > 0.8 * total:
@@ -154,6 +162,8 @@ class Engine:
             cap = int(capacity) if capacity is not None else int(min(n * G, max(n * self.rows_per_ray_hint * 1.05, 4096)))
             cap = max(cap, 1)
             late_gather = to_host and zero_copy  # the gather writes into a host frame sized from the row count
+            if late_gather and fp32:
+                raise _lib.PrtError("zero_copy is an FP64-path experiment; use to_host=True with precision='fp32'")
             while True:
                 stage = self._buf("stage", _lib.STAGE_COLS * cap, torch.float64)
                 run_start = self._buf("run_start", G * n_tiles, torch.int64)
@@ -178,7 +188,8 @@ class Engine:
                     # staging buffer (rows <= cap whenever nothing was dropped), the kernel takes the row
                     # offsets from device memory, and the step has one host synchronisation, at its end
                     frame = torch.empty((_lib.FRAME_COLS, cap), dtype=torch.float64, device=self._dev())
-                    self._gather_into(rec, d_rays, G, gen_off, frame, cap)
+                    self._gather_into(rec, d_rays, G, gen_off, frame, cap,
+                                      layout=_lib.LAYOUT_FP32_RECORDS if fp32 else 0)
                     launches += 1
                 host = torch.cat([ctr, gen_off[: G + 1]]).cpu()  # one small D2H + sync
                 counters = dict(zip(_lib.COUNTER_FIELDS, (int(x) for x in host[: len(_lib.COUNTER_FIELDS)])))

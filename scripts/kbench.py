@@ -17,6 +17,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else "config4"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 22
 wl = workloads.WORKLOADS[name]
 eng = pyrayt_b200.Engine(wl.scene(), 0)
+PREC = os.environ.get("KBENCH_PRECISION", "fp64")
+if PREC != "fp64":  # every trace below runs the fast mode
+    _trace = eng.trace
+    eng.trace = lambda *a, **k: _trace(*a, precision=PREC, **k)
 rays = wl.source.generate(n, device=0)
 if os.environ.get("KBENCH_ONLY") == "k1":  # profiling runs: three recording traces and nothing else
     for it in range(3):

@@ -16,7 +16,7 @@ def lib():
         so = os.path.join(_HERE, "libprt_emul.so")
         srcs = [os.path.join(_HERE, "prt_emul.cpp")] + [
             os.path.join(_HERE, "..", "..", "pyrayt_b200", "csrc", f)
-            for f in ("prt_device.cuh", "prt_encode.h", "prt_scene.h")]
+            for f in ("prt_device.cuh", "prt_device_f32.cuh", "prt_encode.h", "prt_scene.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so,
                                    srcs[0]])
@@ -48,6 +48,28 @@ def trace(scene, rays, generation_limit, ray_offset=1e-6, diagnose=False):
     names = ("rays", "generations", "segments", "tie_rays", "untraceable_hits", "nan_rays", "limit_rays",
              "grazing_rays", "seam_rays")
     return rows[order].T.copy(), dict(zip(names, [int(x) for x in ctr[:9]]))
+
+
+def trace_f32(scene, rays, generation_limit, ray_offset=1e-6):
+    """The FP32 fast mode's per-ray code on the host: frame (15, rows) ordered (generation, input order)."""
+    rays = np.ascontiguousarray(rays, dtype=np.float64)
+    n = rays.shape[1]
+    cap = max(1, n * generation_limit)
+    rows = np.empty((cap, 15))
+    nrows = np.zeros(max(n, 1), dtype=np.int32)
+    desc = scene.as_desc()
+    L = lib()
+    L.prt_emul_trace_f32.restype = ctypes.c_longlong
+    total = L.prt_emul_trace_f32(ctypes.byref(desc), rays.ctypes.data_as(_dp), ctypes.c_longlong(n),
+                                 ctypes.c_longlong(n), ctypes.c_int(generation_limit), ctypes.c_double(ray_offset),
+                                 rows.ctypes.data_as(_dp), ctypes.c_longlong(cap),
+                                 nrows.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    if total == -5:
+        return None
+    assert total >= 0
+    rows = rows[:total]
+    rnd = np.concatenate([np.arange(k) for k in nrows[:n]]) if total else np.zeros(0, dtype=np.int64)
+    return rows[np.argsort(rnd, kind="stable")].T.copy()
 
 
 def intersect(scene, component, rays):

@@ -16,6 +16,7 @@ using std::isnan;
 #include "../../pyrayt_b200/csrc/prt_device.cuh"
 #include "../../pyrayt_b200/csrc/prt_literal.cuh"
 #include "../../pyrayt_b200/csrc/prt_encode.h"
+#include "../../pyrayt_b200/csrc/prt_device_f32.cuh"
 
 static int g_diagnose = 0;
 
@@ -101,6 +102,61 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
   counters[6] = lims;
   counters[7] = graze;
   counters[8] = seam;
+  return total;
+}
+
+// The FP32 fast mode's per-ray code (prt_device_f32.cuh) on the host: same driver loop as trace_kernel_f32,
+// rows expanded as gather_kernel_f32 does.  (The host compiler does not contract to FMA, so values differ
+// from the device in the last bits; the mode's contract is a tolerance.)  Returns rows, -1 bad scene,
+// -5 when the scene needs the generic interpreter (unsupported in this mode).
+long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long long n, long long stride,
+                             int generation_limit, double ray_offset, double* rows_out, long long cap, int* nrows) {
+  std::vector<unsigned char> blob;
+  std::vector<int> slots;
+  std::string err;
+  if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
+  const prt::SceneView sv = prt::make_view(blob.data());
+  if (sv.h->flags & 2) return -5;
+  std::vector<prt::f32::LeafF> lf(sv.h->n_leaves);
+  std::vector<prt::f32::CompF> cf(sv.h->n_components);
+  for (int l = 0; l < sv.h->n_leaves; ++l) prt::f32::convert_leaf(sv.leaves[l], lf[l]);
+  for (int c = 0; c < sv.h->n_components; ++c) prt::f32::convert_comp(sv.comps[c], cf[c]);
+  prt::f32::SceneViewF sc = {sv.h, sv.comps, sv.leaves, lf.data(), cf.data()};
+  long long total = 0;
+  for (long long i = 0; i < n; ++i) {
+    prt::f32::RayStateF r = {(float)rays[0 * stride + i], (float)rays[1 * stride + i], (float)rays[2 * stride + i],
+                             (float)rays[4 * stride + i], (float)rays[5 * stride + i], (float)rays[6 * stride + i],
+                             (float)rays[10 * stride + i], (float)rays[11 * stride + i], -1, -1};
+    const double gen0 = rays[8 * stride + i], inten = rays[9 * stride + i], id = rays[12 * stride + i];
+    const double wl = rays[10 * stride + i];
+    prt::StepCounters c = {0, 0};
+    int k = 0;
+    for (int g = 0; g < generation_limit; ++g) {
+      const float vn = prt::f32::step_speed(r, c);
+      if (vn == 0.0f) break;
+      float t;
+      int leaf;
+      bool tie = false;
+      prt::f32::nearest_hit(sc, r, prt::f32::ray_scale(r), t, leaf, tie);
+      if (leaf < 0) break;
+      if (lf[leaf].mat == PRT_MAT_UNTRACEABLE) break;
+      if (total < cap) {
+        double* w = rows_out + total * 15;
+        const float rv = 1.0f / std::sqrt(r.v0 * r.v0 + r.v1 * r.v1 + r.v2 * r.v2);
+        w[0] = (g == 0) ? gen0 : (double)g; w[1] = inten; w[2] = wl; w[3] = (double)r.nidx; w[4] = id;
+        w[5] = sv.leaves[leaf].sid;
+        w[6] = r.p0; w[7] = r.p1; w[8] = r.p2;
+        w[9] = r.p0 + r.v0 * t; w[10] = r.p1 + r.v1 * t; w[11] = r.p2 + r.v2 * t;
+        w[12] = r.v0 * rv; w[13] = r.v1 * rv; w[14] = r.v2 * rv;
+      }
+      ++total;
+      ++k;
+      prt::f32::StepOutF o;
+      if (!prt::f32::step_interact(sc, r, g, generation_limit, vn, t, leaf, o, c)) break;
+      prt::f32::advance_ray(r, o, leaf, (float)ray_offset);
+    }
+    nrows[i] = k;
+  }
   return total;
 }
 
@@ -200,7 +256,7 @@ long long prt_emul_selfcheck_left_deep(long long* cases_out) {
         // closed form, shape 2: (A op1 B), C absent
         double ct; int cl; bool t2 = false;
         if (op2 == 1 && ic0 == 0 && ic1 == 0) {
-          prt::left_deep_first_hit(tt2, a[0], a[1], b[0], b[1], INFINITY, INFINITY, 10, 11, -1, ct, cl, t2);
+          prt::left_deep_first_hit(tt2, a[0], a[1], b[0], b[1], (double)INFINITY, (double)INFINITY, 10, 11, -1, ct, cl, t2);
           if (!(ct == want2 && cl == wl2) || (tie2 && !t2)) ++bad;
         }
         // closed form, shape 3

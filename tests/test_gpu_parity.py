@@ -62,6 +62,64 @@ def test_diagnose_counters_match_the_oracle(cuda_device):
         assert plain.counters["grazing_rays"] == 0 and plain.counters["seam_rays"] == 0
 
 
+FP32_CASES = [c for c in GOLDEN_CASES if c != "nested_csg"]  # nested_csg needs the generic interpreter
+
+
+@pytest.mark.parametrize("name", FP32_CASES)
+def test_fp32_fast_mode_within_its_tolerance(name, cuda_device):
+    """Engine.trace(precision="fp32") against the FP64 oracle frame: at most 0.5 % of the rays of these
+    edge-case-heavy sets take another path; on the others the id columns are equal, positions agree to 1e-5 of
+    the scene scale, unit tilts and the refractive index to 1e-5 (the tolerance the north star states)."""
+    import torch
+
+    from oracle import oracle
+    from pyrayt_b200 import compare
+
+    scene, rays, _, gl = load_case(name)
+    eng, res = _trace(scene, rays, gl, precision="fp32")
+    want, octr = oracle.trace(scene, rays, gl)
+    first = int(rays[12].min())
+    rep = compare.frame_agreement(torch.from_numpy(want).cuda(), res.frame, first, rays.shape[1])
+    assert rep["rays_with_a_different_path"] <= max(1, int(0.005 * rays.shape[1])), rep
+    assert rep["id_columns_equal_on_compared_rows"], rep
+    assert rep["max_position_error_rel_scale"] <= 1e-5, rep
+    assert rep["max_tilt_error"] <= 1e-5 and rep["max_index_error"] <= 1e-5, rep
+    assert res.counters["segments"] == res.rows and res.counters["rows_dropped"] == 0
+    # rows in (generation, id) order like the FP64 frame
+    f = res.frame.cpu().numpy()
+    key = f[0] * 1e9 + f[4]
+    assert np.all(np.diff(key) > 0)
+    # the host transfer path serves this frame too
+    host = eng.trace(torch.from_numpy(np.ascontiguousarray(rays)).cuda(), generation_limit=gl, precision="fp32",
+                     to_host=True)
+    assert np.array_equal(host.frame.numpy(), f, equal_nan=True)
+
+
+def test_fp32_fast_mode_limits(cuda_device):
+    import torch
+
+    import pyrayt_b200
+
+    scene, rays, _, gl = load_case("nested_csg")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    d = torch.from_numpy(np.ascontiguousarray(rays)).cuda()
+    with pytest.raises(pyrayt_b200.PrtError, match="FP32 fast mode"):
+        eng.trace(d, generation_limit=gl, precision="fp32")
+    with pytest.raises(ValueError):
+        eng.trace(d, generation_limit=gl, precision="fp16")
+    scene, rays, _, gl = load_case("config4_stack")
+    eng = pyrayt_b200.Engine(scene, device=0)
+    d = torch.from_numpy(np.ascontiguousarray(rays)).cuda()
+    with pytest.raises(pyrayt_b200.PrtError, match="FP64 diagnostic"):
+        eng.trace(d, generation_limit=gl, precision="fp32", diagnose=True)
+    # counters-only and empty input
+    none = eng.trace(d, generation_limit=gl, precision="fp32", record="none")
+    full = eng.trace(d, generation_limit=gl, precision="fp32")
+    assert none.counters["segments"] == full.rows and none.counters["generations"] == full.counters["generations"]
+    empty = eng.trace(d[:, :0], generation_limit=gl, precision="fp32")
+    assert empty.rows == 0
+
+
 def test_edge_inputs(cuda_device):
     """Empty input, one ray, generation_limit 1, ray counts around the tile size, dead-on-arrival rays."""
     import torch
