@@ -199,7 +199,7 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
       return fail(PRT_ERR_UNSUPPORTED, "the FP32 fast mode traces bare surfaces and left-deep CSG trees of up to three "
                                        "leaves (everything the reference's factories build); this scene needs FP64");
     if (p->flags & PRT_FLAG_DIAGNOSE) return fail(PRT_ERR_UNSUPPORTED, "PRT_FLAG_DIAGNOSE is an FP64 diagnostic");
-    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 100 * 1024)
+    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 72 * 1024)
       return fail(PRT_ERR_LIMIT, "scene too large for the FP32 fast mode's shared-memory staging");
     cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->n_leaves, scene->n_components,
                                            (cudaStream_t)cuda_stream);
@@ -223,6 +223,7 @@ int prt_trace_wavefront(prt_scene* scene, const prt_params* p, const double* d_r
   if (p->generation_limit > 65535) return fail(PRT_ERR_LIMIT, "generation_limit must be <= 65535");
   if (p->record_mode != PRT_RECORD_ALL && p->record_mode != PRT_RECORD_SURFACE)
     return fail(PRT_ERR_INVALID, "the wavefront trace records rows: record_mode must be ALL or SURFACE");
+  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   const int64_t tiles = (n_rays + prt_wave_tile() - 1) / prt_wave_tile();
   if (tiles > 0x7fffffffLL) return fail(PRT_ERR_LIMIT, "too many rays for one launch");
   if (ws->n_tiles < tiles) return fail(PRT_ERR_INVALID, "workspace.n_tiles too small");
@@ -317,6 +318,7 @@ int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int
   if (slots_out) *slots_out = slots;
   if (n == 0) return PRT_OK;
   if (!d_rays || !d_hits || !d_sids) return fail(PRT_ERR_INVALID, "null buffer");
+  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   cudaError_t e = prt_launch_intersect(scene->d_blob, scene->blob_bytes, component, d_rays, n, d_hits,
                                        reinterpret_cast<long long*>(d_sids), slots, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "intersect kernel launch");
@@ -329,6 +331,7 @@ int prt_nearest_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d
   if (n < 0) return fail(PRT_ERR_INVALID, "negative ray count");
   if (n == 0) return PRT_OK;
   if (!d_rays || !d_t || !d_sid) return fail(PRT_ERR_INVALID, "null buffer");
+  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   cudaError_t e = prt_launch_nearest(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
                                      reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "nearest kernel launch");
@@ -341,6 +344,7 @@ int prt_render_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d_
   if (n < 0) return fail(PRT_ERR_INVALID, "negative ray count");
   if (n == 0) return PRT_OK;
   if (!d_rays || !d_t || !d_sid) return fail(PRT_ERR_INVALID, "null buffer");
+  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   cudaError_t e = prt_launch_render_hit(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
                                         reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "render hit kernel launch");

@@ -600,7 +600,7 @@ PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double&
 
 struct HitStack {
   double t[kMaxDepth * 2][kMaxSlots];
-  unsigned char leaf[kMaxDepth * 2][kMaxSlots];
+  unsigned short leaf[kMaxDepth * 2][kMaxSlots];
   int len[kMaxDepth];
   unsigned flags;  // bit s: which of the two buffers of level s is live
 };
@@ -640,7 +640,7 @@ PRT_HD void merge_lists(HitStack& S, int lvl, int op, int nR, GetRT r_t, GetRL r
     const bool keep = is_union ? ((cnt != 0) != (prev != 0)) : (cnt == 2 || prev == 2);
     if (keep) {
       S.t[dst][k] = takeL ? tl : tr;
-      S.leaf[dst][k] = takeL ? S.leaf[src][i] : (unsigned char)r_leaf(j);
+      S.leaf[dst][k] = takeL ? S.leaf[src][i] : (unsigned short)r_leaf(j);
       ++k;
     }
     if (takeL)
@@ -683,8 +683,8 @@ PRT_HD bool eval_component(const SceneView& sc, int begin, int end, double p0, d
       const int n = (t0 < PRT_INF) ? ((t1 < PRT_INF) ? 2 : 1) : 0;
       S.t[b][0] = t0;
       S.t[b][1] = t1;
-      S.leaf[b][0] = (unsigned char)op.a;
-      S.leaf[b][1] = (unsigned char)op.a;
+      S.leaf[b][0] = (unsigned short)op.a;
+      S.leaf[b][1] = (unsigned short)op.a;
       S.len[sp++] = n;
     } else if (op.kind == OP_MERGE_LEAF) {
       double t0, t1;

@@ -152,7 +152,6 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   if (d->n_components < 0 || d->n_nodes < 0 || d->n_leaves < 0) return fail(PRT_ERR_INVALID, "negative counts");
   if (d->n_leaves > PRT_MAX_LEAVES || d->n_nodes > PRT_MAX_NODES)
     return fail(PRT_ERR_LIMIT, "scene exceeds PRT_MAX_LEAVES / PRT_MAX_NODES");
-  if (d->n_leaves > 255) return fail(PRT_ERR_LIMIT, "leaf index must fit one byte");
 
   Encoder enc;
   enc.s = d;

@@ -37,7 +37,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #define PRT_MIN_BLOCKS 2
 #endif
 
-template <bool RECORD, bool GENERIC, bool DIAG = false>
+template <bool RECORD, bool GENERIC, bool DIAG = false, bool GLOBAL = false>
 __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char s_blob[];
   __shared__ int s_wcount[kTileRays / 32];
@@ -48,15 +48,16 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
   __shared__ double s_wl[kTileRays], s_nidx[kTileRays];
   __shared__ unsigned s_ctr0[kTileRays], s_ctr1[kTileRays];
 
-  // stage the scene in shared memory once per block
-  {
+  // stage the scene in shared memory once per block (GLOBAL: a scene too large for that is read in place,
+  // through L1 / L2 -- the ordered traversal touches a few components per ray and generation)
+  if (!GLOBAL) {
     const int words = a.blob_bytes / 8;
     const double* src = reinterpret_cast<const double*>(a.blob);
     double* dst = reinterpret_cast<double*>(s_blob);
     for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
   }
   __syncthreads();
-  const SceneView sc = make_view(s_blob);
+  const SceneView sc = make_view(GLOBAL ? a.blob : s_blob);
 
   const long long tile = blockIdx.x;
   const long long i = tile * kTileRays + threadIdx.x;
@@ -661,6 +662,16 @@ extern "C" {
 cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, int diagnose, cudaStream_t st) {
   const long long tiles = (a->n_rays + prt::kTileRays - 1) / prt::kTileRays;
   if (tiles == 0) return cudaSuccess;
+  if (a->blob_bytes > prt::kMaxSharedBlob) {  // large scene: read from global memory, interpreter variant
+    if (diagnose) {
+      if (record) prt::trace_kernel<true, true, true, true><<<(unsigned)tiles, prt::kTileRays, 0, st>>>(*a);
+      else prt::trace_kernel<false, true, true, true><<<(unsigned)tiles, prt::kTileRays, 0, st>>>(*a);
+    } else {
+      if (record) prt::trace_kernel<true, true, false, true><<<(unsigned)tiles, prt::kTileRays, 0, st>>>(*a);
+      else prt::trace_kernel<false, true, false, true><<<(unsigned)tiles, prt::kTileRays, 0, st>>>(*a);
+    }
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)a->blob_bytes;
   if (diagnose)
     return record ? launch_trace_variant<true, true, true>(a, (unsigned)tiles, smem, st)

@@ -33,6 +33,9 @@ constexpr double kCullMargin = 1e-7;
 // Smaller scenes keep the list-order loop: every lane of a warp then looks at the same component in the same
 // iteration, which keeps the primitive switch uniform when the few components are of different kinds.
 constexpr int kOrderedMinBoxed = 8;
+// Encoded scenes up to this size are staged in shared memory by every block of the trace kernel (two blocks
+// per SM share 228 KB); larger ones are read from global memory through L1 / L2 (trace_kernel<.., GLOBAL>).
+constexpr int kMaxSharedBlob = 100 * 1024;
 
 enum OpKind : int {
   OP_LEAF = 0,        // a = leaf              : push the leaf's hit pair

@@ -33,8 +33,8 @@ NODE_LEAF, NODE_UNION, NODE_INTERSECT, NODE_DIFFERENCE = 0, 1, 2, 3
 MAT_ABSORBER, MAT_MIRROR, MAT_GLASS_CONST, MAT_GLASS_SELLMEIER, MAT_UNTRACEABLE = 0, 1, 2, 3, 4
 
 MAX_SLOTS = 32
-MAX_LEAVES = 128
-MAX_NODES = 256
+MAX_LEAVES = 4096  # PRT_MAX_LEAVES
+MAX_NODES = 8192  # PRT_MAX_NODES
 
 
 class SceneError(ValueError):

@@ -237,3 +237,38 @@ def grazing_and_seam_case():
     # ray 5: plane a <-> nothing
     expected = [(0, 1), (0, 1), (0, 0), (0, 1), (0, 0), (1, 0)]
     return scene, rays, expected
+
+
+def lenslet_array(nx, ny, pitch=2.0, radius=0.9, thickness=0.6, curvature=3.0, index=1.5):
+    """nx x ny biconvex lenslets in the plane x = 0 (each cylinder & sphere & sphere, a left-deep tree with
+    tight boxes) and an absorbing detector behind them: 3 nx ny + 1 leaves.  Returns (scene, lens centres)."""
+    comps, centres = [], []
+    for i in range(nx):
+        for j in range(ny):
+            cy, cz = (i - (nx - 1) / 2) * pitch, (j - (ny - 1) / 2) * pitch
+            centres.append((cy, cz))
+            cyl = Leaf(CYLINDER, [radius, -thickness / 2, thickness / 2, 1.0], mat=MAT_GLASS_CONST, matp=[index],
+                       world=translate(0, cy, cz) @ rot_y(90))
+            s_a = Leaf(SPHERE, [curvature], mat=MAT_GLASS_CONST, matp=[index],
+                       world=translate(-thickness / 2 + curvature, cy, cz))
+            s_b = Leaf(SPHERE, [curvature], mat=MAT_GLASS_CONST, matp=[index],
+                       world=translate(thickness / 2 - curvature, cy, cz))
+            inner = intersect(cyl, s_a)
+            inner.aabb = tuple(tight_box(inner).reshape(6))
+            lens = intersect(inner, s_b)
+            lens.aabb = tuple(tight_box(lens).reshape(6))
+            comps.append(lens)
+    size = pitch * max(nx, ny) * 2
+    comps.append(Leaf(PLANE, [size, size], world=translate(12.0, 0, 0) @ rot_y(90)))
+    return build(comps), np.asarray(centres)
+
+
+def lenslet_rays(centres, per_lens, seed=0, spread=0.8):
+    """Rays from x = -5 aimed at random points of every lenslet, slightly tilted."""
+    rng = np.random.default_rng(seed)
+    c = np.repeat(centres, per_lens, axis=0)
+    n = c.shape[0]
+    o = np.column_stack([np.full(n, -5.0), c[:, 0] + rng.uniform(-spread, spread, n), c[:, 1] + rng.uniform(-spread, spread, n)])
+    d = np.column_stack([np.ones(n), rng.normal(0, 0.05, n), rng.normal(0, 0.05, n)])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return make_rays(o, d)

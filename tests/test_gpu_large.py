@@ -416,12 +416,15 @@ def test_wavefront_trace_is_bit_identical_to_single_kernel_trace(torch_mod):
         assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), n
 
 
-@pytest.mark.parametrize("name,n,max_bad_fraction", [("config2", 1 << 20, 1e-4), ("config3", 1 << 20, 1e-4),
+@pytest.mark.parametrize("name,n,max_bad_fraction", [("config2", 1 << 20, 1e-3), ("config3", 1 << 20, 1e-4),
                                                      ("config4", 1 << 20, 1e-4), ("config5", 1 << 20, 2e-2)])
 def test_fp32_fast_mode_on_the_workloads(name, n, max_bad_fraction, torch_mod):
     """The optional FP32 fast mode against the FP64 frame of the same rays at a million rays per workload:
     positions within 1e-5 of the scene scale, tilts / index within 1e-5, id columns equal, on all rays but the
-    few that pass within the tolerance of an edge (config 5's sixteen-bounce light pipe amplifies those)."""
+    few that pass within the tolerance of an edge (config 5's sixteen-bounce light pipe amplifies those) or of
+    one of the reference's own decision thresholds: in config 2 the condenser collimates the beam to ~1e-7 rad,
+    where binomial_root's isclose(b, 0) (atol 1e-8, operations.py:45-52) decides whether the stop's cylinder is
+    "missed" -- a threshold below single-precision resolution, 4.5e-4 of the rays sit on the other side of it."""
     from pyrayt_b200 import compare
 
     wl, eng = _engine(name)
@@ -434,3 +437,35 @@ def test_fp32_fast_mode_on_the_workloads(name, n, max_bad_fraction, torch_mod):
     assert rep["id_columns_equal_on_compared_rows"], rep
     assert rep["max_position_error_rel_scale"] <= 1e-5, rep
     assert rep["max_tilt_error"] <= 1e-5 and rep["max_index_error"] <= 1e-5, rep
+
+
+def test_lenslet_array_of_973_leaves_is_read_from_global_memory(torch_mod):
+    """A 973-leaf scene (18 x 18 lenslets + detector): its encoded form (several hundred KB) does not fit a
+    block's shared memory, so the trace kernel reads it in place through L1 / L2 (trace_kernel<.., GLOBAL>).
+    Frame bit-equal to the oracle, counters-only and diagnosing traces agree, the entry points that only stage
+    in shared memory refuse it with PRT_ERR_LIMIT."""
+    import pyrayt_b200
+    from oracle import oracle
+    from tests import scene_util as su
+
+    torch = torch_mod
+    scene, centres = su.lenslet_array(18, 18)
+    rays = su.lenslet_rays(centres, 64)  # 20,736 rays
+    eng = pyrayt_b200.Engine(scene, device=0)
+    d = torch.from_numpy(rays).cuda()
+    res = eng.trace(d, generation_limit=8, to_host=True)
+    want, octr = oracle.trace(scene, rays, 8, threads=THREADS)
+    assert np.array_equal(res.frame.numpy(), want, equal_nan=True)
+    assert res.counters["generations"] == octr["generations"]
+    none = eng.trace(d, generation_limit=8, record="none")
+    assert none.counters["segments"] == res.rows
+    sub = np.ascontiguousarray(rays[:, :2048])
+    diag = eng.trace(torch.from_numpy(sub).cuda(), generation_limit=8, diagnose=True)
+    o = oracle.diagnose(scene, sub, 8, threads=THREADS)
+    assert (diag.counters["grazing_rays"], diag.counters["seam_rays"]) == (o["grazing_rays"], o["seam_rays"])
+    with pytest.raises(pyrayt_b200.PrtError, match="too large"):
+        eng.nearest_hit(torch.zeros((2, 4, 8), dtype=torch.float64, device="cuda"))
+    with pytest.raises(pyrayt_b200.PrtError, match="too large"):
+        eng.trace(d, generation_limit=8, precision="fp32")
+    with pytest.raises(pyrayt_b200.PrtError, match="too large"):
+        eng.trace_wavefront(d, generation_limit=8)

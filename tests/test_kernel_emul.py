@@ -164,3 +164,16 @@ def test_fp32_fast_mode_code_within_its_tolerance(name):
 def test_fp32_fast_mode_refuses_generic_trees():
     scene, rays, _, gl = load_case("nested_csg")
     assert emul.trace_f32(scene, rays, gl) is None
+
+
+def test_lenslet_array_of_973_leaves():
+    """A scene far beyond the reference's examples: 18 x 18 lenslets (972 leaves in 324 left-deep components)
+    and a detector.  16-bit leaf indices, the ray-ordered traversal with bisection over 324 boxes."""
+    scene, centres = su.lenslet_array(18, 18)
+    assert scene.n_leaves == 973 and scene.n_components == 325
+    rays = su.lenslet_rays(centres, 2)
+    want, octr = oracle.trace(scene, rays, 8, threads=4)
+    got, ectr = emul.trace(scene, rays, 8)
+    assert want.shape[1] > 2 * rays.shape[1]
+    assert np.array_equal(got, want, equal_nan=True)
+    assert ectr["generations"] == octr["generations"]
