@@ -102,7 +102,10 @@ PRT_HD_CALL double slow_div(double a, double b) { return a / b; }
 
 PRT_HD double div_by(double a, const Rcp& R) {
   if (exp_of(a) - kExpLo < R.lim) return div_fast(a, R);
-  return slow_div(a, R.b);  // zero, tiny, huge, inf, NaN or an unsafe denominator: one shared IEEE division
+  // a zero numerator over a safe denominator (the zero components of an axis-aligned normal: every cuboid
+  // face, every plane): the quotient is the correctly signed zero a * r
+  if ((a == 0.0) & (R.lim != 0u)) return a * R.r;
+  return slow_div(a, R.b);  // tiny, huge, inf, NaN or an unsafe denominator: one shared IEEE division
 }
 
 // Two / three quotients by the same denominator: the 3-instruction form is computed for all of them

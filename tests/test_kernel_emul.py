@@ -155,10 +155,9 @@ def test_fp32_fast_mode_code_within_its_tolerance(name):
     first = int(rays[12].min())
     assert np.array_equal(np.sort(rays[12]), np.arange(first, first + rays.shape[1]))
     rep = compare.frame_agreement(torch.from_numpy(want), torch.from_numpy(got), first, rays.shape[1])
-    assert rep["rays_with_a_different_path"] <= max(1, int(0.005 * rays.shape[1])), rep
+    assert rep["rays_with_different_ids"] + rep["rays_beyond_tolerance"] <= max(1, int(0.005 * rays.shape[1])), rep
     assert rep["id_columns_equal_on_compared_rows"], rep
-    assert rep["max_position_error_rel_scale"] <= 1e-5, rep
-    assert rep["max_tilt_error"] <= 1e-5 and rep["max_index_error"] <= 1e-5, rep
+    assert rep["max_error_on_agreeing_rays"] <= 1e-5, rep
 
 
 def test_fp32_fast_mode_refuses_generic_trees():
