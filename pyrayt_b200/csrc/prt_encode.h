@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -328,6 +329,11 @@ inline int encode_scene(const prt_scene_desc* d, std::vector<unsigned char>& blo
   h.off_bycomp = off;
   off += (int)sizeof(prt::OrderEntry) * 6 * (d->n_components > 0 ? d->n_components : 1);
   if (h.n_boxed > prt::kOrderedMinBoxed) h.flags |= 8;
+  // experiments only: PRT_FORCE_TRAVERSAL=ordered|list overrides the choice (both give the same frame)
+  if (const char* force = std::getenv("PRT_FORCE_TRAVERSAL")) {
+    if (force[0] == 'o' && h.n_boxed > 0) h.flags |= 8;
+    if (force[0] == 'l') h.flags &= ~8;
+  }
   h.total_bytes = off;
   blob.assign((size_t)off, 0);
   std::memcpy(blob.data(), &h, sizeof h);

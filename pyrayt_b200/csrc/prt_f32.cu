@@ -36,8 +36,12 @@ __device__ __forceinline__ void unpack2(double w, float& a, float& b) {
 // bytes of dynamic shared memory: the FP64 blob, then LeafF[n_leaves], then CompF[n_components]
 __host__ __device__ inline int blob_aligned(int blob_bytes) { return (blob_bytes + 15) & ~15; }
 
+#ifndef PRT_F32_MIN_BLOCKS
+#define PRT_F32_MIN_BLOCKS 3
+#endif
+
 template <bool RECORD>
-__global__ void __launch_bounds__(kTileRays, 3) trace_kernel_f32(const TraceArgs a, int n_leaves, int n_components) {
+__global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f32(const TraceArgs a, int n_leaves, int n_components) {
   extern __shared__ __align__(16) unsigned char s_mem[];
   __shared__ int s_wcount[kTileRays / 32];
   __shared__ long long s_base;

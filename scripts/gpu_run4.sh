@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_r2d.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu_r2d.log
 tail -15 $O/pytest_gpu_r2d.log
-for cfg in "config4 16777216" "config5 33554432" "config2 100000" "config3 1048576"; do
+for cfg in "config4 16777216" "config5 33554432" "config2 100000" "config3 1048586"; do
   timeout 300 python scripts/kbench.py $cfg 2>&1 | grep -v "^$"
   KBENCH_PRECISION=fp32 timeout 300 python scripts/kbench.py $cfg 2>&1 | grep -v "^$" | sed 's/^default/fp32   /'
 done | tee $O/kbench_r2d.txt
