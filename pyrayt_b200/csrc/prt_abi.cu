@@ -199,7 +199,7 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
       return fail(PRT_ERR_UNSUPPORTED, "the FP32 fast mode traces bare surfaces and left-deep CSG trees of up to three "
                                        "leaves (everything the reference's factories build); this scene needs FP64");
     if (p->flags & PRT_FLAG_DIAGNOSE) return fail(PRT_ERR_UNSUPPORTED, "PRT_FLAG_DIAGNOSE is an FP64 diagnostic");
-    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 72 * 1024)
+    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 52 * 1024)
       return fail(PRT_ERR_LIMIT, "scene too large for the FP32 fast mode's shared-memory staging");
     cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->n_leaves, scene->n_components,
                                            (cudaStream_t)cuda_stream);

@@ -37,7 +37,7 @@ __device__ __forceinline__ void unpack2(double w, float& a, float& b) {
 __host__ __device__ inline int blob_aligned(int blob_bytes) { return (blob_bytes + 15) & ~15; }
 
 #ifndef PRT_F32_MIN_BLOCKS
-#define PRT_F32_MIN_BLOCKS 3
+#define PRT_F32_MIN_BLOCKS 4
 #endif
 
 template <bool RECORD>

@@ -5,7 +5,8 @@
     compute-sanitizer --tool synccheck python scripts/sanitize_run.py
 
 Golden cases (all record modes, staging overflow + retry, the wavefront driver, the captured small-trace
-sequence, the lean host transfer), sources, component.intersect, nearest / render hits, the ordering kernels
+sequence, the lean host transfer, the diagnose variant, the FP32 fast mode), a 973-leaf scene read from global
+memory, sources, component.intersect, nearest / render hits, the ordering kernels
 and the frame read-outs; every result is compared with the oracle.
 """
 import os
@@ -47,6 +48,13 @@ for name in GOLDEN_CASES:
     res = eng.trace(d, generation_limit=gl, record="surface", detector_sid=sid)
     assert np.array_equal(res.frame.cpu().numpy(), want[:, want[5] == sid], equal_nan=True), name
     assert eng.trace(d, generation_limit=gl, record="none").counters["generations"] == ctr["generations"]
+    diag = eng.trace(d, generation_limit=gl, diagnose=True)  # PRT_FLAG_DIAGNOSE variant
+    odiag = oracle.diagnose(scene, rays, gl)
+    assert (diag.counters["grazing_rays"], diag.counters["seam_rays"]) == (odiag["grazing_rays"], odiag["seam_rays"]), name
+    if name != "nested_csg":  # the FP32 fast mode: trace + ordering + host transfer
+        f32 = eng.trace(d, generation_limit=gl, precision="fp32", to_host=True)
+        assert abs(f32.rows - want.shape[1]) <= max(2, want.shape[1] // 100), name
+        eng.trace(d, generation_limit=gl, precision="fp32", record="none")
     full = eng.trace(d, generation_limit=gl)
     if full.rows:
         analytics.spot_stats(full, max(1, rays.shape[1] // 3), 3, surface=sid)
@@ -64,6 +72,18 @@ for name in GOLDEN_CASES:
         assert np.array_equal(hits, oh, equal_nan=True) and np.array_equal(sids, os_), name
     eng.close()
     checked += 1
+# a scene too large for shared memory: the trace kernel reads it in place (GLOBAL variant)
+from tests import scene_util as su  # noqa: E402
+
+scene, centres = su.lenslet_array(18, 18)
+rays = su.lenslet_rays(centres, 2)
+eng = pyrayt_b200.Engine(scene, 0)
+res = eng.trace(torch.from_numpy(rays).cuda(), generation_limit=8)
+want, _ = oracle.trace(scene, rays, 8, threads=4)
+assert np.array_equal(res.frame.cpu().numpy(), want, equal_nan=True), "lenslet array"
+eng.trace(torch.from_numpy(rays[:, :256].copy()).cuda(), generation_limit=8, diagnose=True, record="none")
+eng.close()
+checked += 1
 for name in RENDER_CASES:
     scene, rays, dist, surf, _, _ = load_render_case(name)
     eng = pyrayt_b200.Engine(scene, 0)
