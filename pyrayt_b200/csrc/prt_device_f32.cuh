@@ -42,12 +42,20 @@ struct CompF {
   float inner_box[6];
 };
 
+// OrderEntry (prt_scene.h) in single precision: near faces rounded down, far faces up
+struct OrderEntryF {
+  float near_u, far_u, pmfar_u;
+  int comp;
+};
+
 struct SceneViewF {
   const BlobHeader* h;
   const Comp* comps;   // shape, flags, leaves, truth table (integers) from the FP64 blob
   const Leaf* leaves;  // FP64 leaves (surface ids)
   const LeafF* lf;
   const CompF* cf;
+  const OrderEntryF* order;  // [6][n_boxed] ray-ordered traversal tables, or nullptr (list-order walk)
+  const int* unboxed;        // [n_unboxed]
 };
 
 // double -> float, rounded down / up (boxes are rounded outwards so that a single-precision box still
@@ -78,6 +86,12 @@ PRT_HD void convert_leaf(const Leaf& L, LeafF& F) {
   F.type = L.type;
   F.mat = L.mat;
   F.comp = L.comp;
+}
+PRT_HD void convert_order(const OrderEntry& E, OrderEntryF& F) {
+  F.near_u = to_float_dn(E.near_u);
+  F.far_u = to_float_up(E.far_u);
+  F.pmfar_u = to_float_up(E.pmfar_u);
+  F.comp = E.comp;
 }
 PRT_HD void convert_comp(const Comp& C, CompF& F) {
   for (int k = 0; k < 6; ++k) {
@@ -364,14 +378,60 @@ struct RayStateF {
   int self;  // leaf the ray has just interacted with, or -1
 };
 
-// nearest hit over all components in list order (_pyrayt.py:376-386): smallest distance, earliest component
-// on ties.  Components with a proven / conservative box (Comp.flags & 5) are skipped when the box lies behind
-// the ray or beyond the best hit so far; CSG components whose box the ray misses have no hits (csg.py:126-133).
+// one component for nearest_hit: its first positive kept entry (ct, cl), or ct = +inf.  `boxed`: the caller has
+// already dealt with the component's root box (ray-ordered walk); otherwise components with a proven /
+// conservative box (Comp.flags & 5) are skipped when the box lies behind the ray or beyond the best hit so far.
+// A CSG component whose root box the ray misses has no hits either way (csg.py:126-133).
+PRT_HD void eval_comp(const SceneViewF& sc, int c, const RayStateF& r, const RayInvF& inv, float margin,
+                      float self_eps, float best_t, float& ct, int& cl, bool& tie) {
+  const float p0 = r.p0, p1 = r.p1, p2 = r.p2, v0 = r.v0, v1 = r.v1, v2 = r.v2;
+  const Comp& C = sc.comps[c];
+  const CompF& F = sc.cf[c];
+  const int shape = C.shape;
+  ct = PRT_INFF;
+  cl = -1;
+  if (shape == SHAPE_LEAF) {
+    if (C.flags & 4) {  // conservative world box of the bare surface: prune only
+      float b0, b1;
+      box_hits(F.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
+      if (!(b0 < PRT_INFF) || (b1 < -margin) || (b0 > best_t + margin)) return;
+    }
+    float t0, t1;
+    leaf_hits(sc.lf[C.leaf_a], p0, p1, p2, v0, v1, v2, (C.leaf_a == r.self) ? self_eps : 0.0f, t0, t1);
+    ct = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INFF);
+    cl = C.leaf_a;
+    return;
+  }
+  // SHAPE_LEFT2 / SHAPE_LEFT3 (the ABI refuses other trees in this mode)
+  float b0, b1;
+  box_hits(F.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
+  if (!(b0 < PRT_INFF)) return;
+  if ((C.flags & 1) && ((b1 < -margin) || (b0 > best_t + margin))) return;
+  bool inner_hit = true;
+  if (shape == SHAPE_LEFT3) {
+    box_hits(F.inner_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
+    inner_hit = b0 < PRT_INFF;
+  }
+  const int la = C.leaf_a, lb = C.leaf_b, lc = C.leaf_c;
+  float a0 = PRT_INFF, a1 = PRT_INFF, q0 = PRT_INFF, q1 = PRT_INFF, c0 = PRT_INFF, c1 = PRT_INFF;
+  if (inner_hit) {
+    leaf_hits(sc.lf[la], p0, p1, p2, v0, v1, v2, (la == r.self) ? self_eps : 0.0f, a0, a1);
+    leaf_hits(sc.lf[lb], p0, p1, p2, v0, v1, v2, (lb == r.self) ? self_eps : 0.0f, q0, q1);
+  }
+  if (shape == SHAPE_LEFT3) leaf_hits(sc.lf[lc], p0, p1, p2, v0, v1, v2, (lc == r.self) ? self_eps : 0.0f, c0, c1);
+  left_deep_first_hit((unsigned)C.tt, a0, a1, q0, q1, c0, c1, la, lb, lc, ct, cl, tie);
+}
+
+// nearest hit over all components (_pyrayt.py:376-386): smallest distance, earliest component on ties -- a
+// result that does not depend on the visiting order.  With traversal tables (sc.order) the boxed components are
+// visited in the order the ray meets them along its dominant axis, as in the FP64 path (prt_device.cuh,
+// nearest_hit): everything behind the ray is skipped by bisection and the walk stops at the first box that
+// begins beyond the best hit.  Otherwise, and for rays the threshold tests cannot serve, list order.
 PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, float& best_t, int& best_leaf,
                         bool& tie) {
   best_t = PRT_INFF;
   best_leaf = -1;
-  const float p0 = r.p0, p1 = r.p1, p2 = r.p2, v0 = r.v0, v1 = r.v1, v2 = r.v2;
+  const float v0 = r.v0, v1 = r.v1, v2 = r.v2;
   RayInvF inv;
   inv.ok = !(isz(v0) | isz(v1) | isz(v2));
   inv.r0 = frcp(v0);
@@ -380,46 +440,58 @@ PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, f
   const float margin = kCullMarginF * scale;
   const float self_eps = kSelfEps * scale;
   const int nc = sc.h->n_components;
-  for (int c = 0; c < nc; ++c) {
-    if (c == r.skip) continue;
-    const Comp& C = sc.comps[c];
-    const CompF& F = sc.cf[c];
-    const int shape = C.shape;
-    float ct = PRT_INFF;
-    int cl = -1;
-    if (shape == SHAPE_LEAF) {
-      if (C.flags & 4) {  // conservative world box of the bare surface: prune only
-        float b0, b1;
-        box_hits(F.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
-        if (!(b0 < PRT_INFF) || (b1 < -margin) || (b0 > best_t + margin)) continue;
-      }
-      float t0, t1;
-      leaf_hits(sc.lf[C.leaf_a], p0, p1, p2, v0, v1, v2, (C.leaf_a == r.self) ? self_eps : 0.0f, t0, t1);
-      ct = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INFF);
-      cl = C.leaf_a;
-    } else {  // SHAPE_LEFT2 / SHAPE_LEFT3 (the ABI refuses other trees in this mode)
-      float b0, b1;
-      box_hits(F.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
-      if (!(b0 < PRT_INFF)) continue;  // csg.py:126-133
-      if ((C.flags & 1) && ((b1 < -margin) || (b0 > best_t + margin))) continue;
-      bool inner_hit = true;
-      if (shape == SHAPE_LEFT3) {
-        box_hits(F.inner_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
-        inner_hit = b0 < PRT_INFF;
-      }
-      const int la = C.leaf_a, lb = C.leaf_b, lc = C.leaf_c;
-      float a0 = PRT_INFF, a1 = PRT_INFF, q0 = PRT_INFF, q1 = PRT_INFF, c0 = PRT_INFF, c1 = PRT_INFF;
-      if (inner_hit) {
-        leaf_hits(sc.lf[la], p0, p1, p2, v0, v1, v2, (la == r.self) ? self_eps : 0.0f, a0, a1);
-        leaf_hits(sc.lf[lb], p0, p1, p2, v0, v1, v2, (lb == r.self) ? self_eps : 0.0f, q0, q1);
-      }
-      if (shape == SHAPE_LEFT3)
-        leaf_hits(sc.lf[lc], p0, p1, p2, v0, v1, v2, (lc == r.self) ? self_eps : 0.0f, c0, c1);
-      left_deep_first_hit((unsigned)C.tt, a0, a1, q0, q1, c0, c1, la, lb, lc, ct, cl, tie);
+  int best_comp = -1;
+  // dominant axis (DomAxis of the FP64 path)
+  const float a0 = fabsf(v0), a1 = fabsf(v1), a2 = fabsf(v2);
+  const int k = (a0 >= a1) ? ((a0 >= a2) ? 0 : 2) : ((a1 >= a2) ? 1 : 2);
+  const float a = (k == 0) ? a0 : ((k == 1) ? a1 : a2);
+  const float o = (k == 0) ? r.p0 : ((k == 1) ? r.p1 : r.p2);
+  const float vk = (k == 0) ? v0 : ((k == 1) ? v1 : v2);
+  const int sgn = vk < 0 ? 1 : 0;
+  const bool ordered = (sc.order != nullptr) & (fabsf(o) <= 1e6f) & (a >= 0.25f) & (a <= 4.0f);
+  // one loop, one call site of eval_comp: phase 0 walks the ray-ordered table, phase 1 the components without
+  // a box, phase 2 (instead of both) every component in list order
+  const int n0 = ordered ? sc.h->n_boxed : 0, n1 = ordered ? sc.h->n_unboxed : nc;
+  const OrderEntryF* tab = ordered ? sc.order + (2 * k + sgn) * n0 : nullptr;
+  const float thr_far = (sgn ? -o : o) - 3 * margin * a;  // boxes ending before it lie behind the ray
+  float thr_near = PRT_INFF;                               // boxes beginning after it lie beyond the best hit
+  int j = 0;
+  if (ordered) {
+    int hi = n0;
+    while (j < hi) {
+      const int mid = (j + hi) >> 1;
+      if (tab[mid].pmfar_u < thr_far) j = mid + 1; else hi = mid;
     }
-    if (ct < best_t) {  // strict: the earlier component keeps a tie (_pyrayt.py:384)
+  }
+  int phase = (j < n0) ? 0 : 1;
+  if (phase) j = 0;
+  for (;;) {
+    int c;
+    if (phase == 0) {
+      const OrderEntryF e = tab[j];
+      const bool beyond = e.near_u > thr_near;  // ray order: every later box begins even further away
+      ++j;
+      if (beyond | (j >= n0)) {
+        phase = 1;
+        j = 0;
+      }
+      if (beyond | (e.far_u < thr_far)) continue;
+      c = e.comp;
+    } else {
+      if (j >= n1) break;
+      c = ordered ? sc.unboxed[j] : j;
+      ++j;
+    }
+    if (c == r.skip) continue;
+    float ct;
+    int cl;
+    eval_comp(sc, c, r, inv, margin, self_eps, best_t, ct, cl, tie);
+    // smallest distance, then earliest component (== the reference's in-order strict `<`, _pyrayt.py:384)
+    if ((ct < best_t) | ((ct == best_t) & (ct < PRT_INFF) & (c < best_comp))) {
       best_t = ct;
       best_leaf = cl;
+      best_comp = c;
+      thr_near = thr_far + (ct + 5 * margin) * a;
     }
   }
 }

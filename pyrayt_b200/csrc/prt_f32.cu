@@ -33,7 +33,7 @@ __device__ __forceinline__ void unpack2(double w, float& a, float& b) {
   b = __uint_as_float((unsigned)(u >> 32));
 }
 
-// bytes of dynamic shared memory: the FP64 blob, then LeafF[n_leaves], then CompF[n_components]
+// bytes of dynamic shared memory: the FP64 blob, then LeafF[n_leaves], CompF[n_components], OrderEntryF[6][n_boxed]
 __host__ __device__ inline int blob_aligned(int blob_bytes) { return (blob_bytes + 15) & ~15; }
 
 #ifndef PRT_F32_MIN_BLOCKS
@@ -57,8 +57,11 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
   __syncthreads();
   LeafF* lf = reinterpret_cast<LeafF*>(s_mem + blob_aligned(a.blob_bytes));
   CompF* cf = reinterpret_cast<CompF*>(lf + n_leaves);
+  OrderEntryF* ordf = reinterpret_cast<OrderEntryF*>(cf + n_components);
   {
     const BlobHeader* h = reinterpret_cast<const BlobHeader*>(s_mem);
+    const OrderEntry* ord = reinterpret_cast<const OrderEntry*>(s_mem + h->off_order);
+    for (int e = threadIdx.x; e < 6 * h->n_boxed; e += blockDim.x) convert_order(ord[e], ordf[e]);
     const Leaf* leaves = reinterpret_cast<const Leaf*>(s_mem + h->off_leaves);
     const Comp* comps = reinterpret_cast<const Comp*>(s_mem + h->off_comps);
     for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) convert_leaf(leaves[l], lf[l]);
@@ -71,6 +74,9 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
   sc.leaves = reinterpret_cast<const Leaf*>(s_mem + sc.h->off_leaves);
   sc.lf = lf;
   sc.cf = cf;
+  // ray-ordered traversal whenever the scene has boxed components inside the quick tests' range (flags bit 2)
+  sc.order = (sc.h->n_boxed > 0 && (sc.h->flags & 4)) ? ordf : nullptr;
+  sc.unboxed = reinterpret_cast<const int*>(s_mem + sc.h->off_unboxed);
 
   const long long tile = blockIdx.x;
   const long long i = tile * kTileRays + threadIdx.x;
@@ -253,7 +259,7 @@ extern "C" {
 // dynamic shared memory of trace_kernel_f32 for a scene
 size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components) {
   return (size_t)prt::f32::blob_aligned(blob_bytes) + (size_t)n_leaves * sizeof(prt::f32::LeafF) +
-         (size_t)n_components * sizeof(prt::f32::CompF);
+         (size_t)n_components * sizeof(prt::f32::CompF) + (size_t)6 * n_components * sizeof(prt::f32::OrderEntryF);
 }
 
 cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int n_leaves, int n_components,

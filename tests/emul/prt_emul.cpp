@@ -121,7 +121,11 @@ long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long l
   std::vector<prt::f32::CompF> cf(sv.h->n_components);
   for (int l = 0; l < sv.h->n_leaves; ++l) prt::f32::convert_leaf(sv.leaves[l], lf[l]);
   for (int c = 0; c < sv.h->n_components; ++c) prt::f32::convert_comp(sv.comps[c], cf[c]);
-  prt::f32::SceneViewF sc = {sv.h, sv.comps, sv.leaves, lf.data(), cf.data()};
+  std::vector<prt::f32::OrderEntryF> ordf(6 * (size_t)sv.h->n_boxed + 1);
+  for (int e = 0; e < 6 * sv.h->n_boxed; ++e) prt::f32::convert_order(sv.order[e], ordf[e]);
+  const bool walk = sv.h->n_boxed > 0 && (sv.h->flags & 4) && !(std::getenv("PRT_EMUL_F32_LIST"));
+  prt::f32::SceneViewF sc = {sv.h, sv.comps, sv.leaves, lf.data(), cf.data(), walk ? ordf.data() : nullptr,
+                             sv.unboxed};
   long long total = 0;
   for (long long i = 0; i < n; ++i) {
     prt::f32::RayStateF r = {(float)rays[0 * stride + i], (float)rays[1 * stride + i], (float)rays[2 * stride + i],

@@ -176,3 +176,17 @@ def test_lenslet_array_of_973_leaves():
     assert want.shape[1] > 2 * rays.shape[1]
     assert np.array_equal(got, want, equal_nan=True)
     assert ectr["generations"] == octr["generations"]
+
+
+def test_fp32_ordered_and_list_walks_agree(monkeypatch):
+    """The FP32 mode's ray-ordered traversal is a reordering of the same per-component evaluations: its frame
+    equals the list-order walk's bit for bit (golden cases and the 973-leaf lenslet array)."""
+    cases = [load_case(n)[:2] + (load_case(n)[3],) for n in FP32_CASES]
+    scene, centres = su.lenslet_array(18, 18)
+    cases.append((scene, su.lenslet_rays(centres, 1), 8))
+    for scene, rays, gl in cases:
+        monkeypatch.delenv("PRT_EMUL_F32_LIST", raising=False)
+        ordered = emul.trace_f32(scene, rays, gl)
+        monkeypatch.setenv("PRT_EMUL_F32_LIST", "1")
+        listed = emul.trace_f32(scene, rays, gl)
+        assert np.array_equal(ordered, listed, equal_nan=True)
