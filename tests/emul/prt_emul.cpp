@@ -123,7 +123,9 @@ long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long l
   for (int c = 0; c < sv.h->n_components; ++c) prt::f32::convert_comp(sv.comps[c], cf[c]);
   std::vector<prt::f32::OrderEntryF> ordf(6 * (size_t)sv.h->n_boxed + 1);
   for (int e = 0; e < 6 * sv.h->n_boxed; ++e) prt::f32::convert_order(sv.order[e], ordf[e]);
-  const bool walk = sv.h->n_boxed > 0 && (sv.h->flags & 4) && !(std::getenv("PRT_EMUL_F32_LIST"));
+  // PRT_EMUL_F32_LIST / PRT_EMUL_F32_ORDERED force one of the two walks (the kernel follows the encoder: flags bit 3)
+  const bool walk = sv.h->n_boxed > 0 && (sv.h->flags & 4) && !std::getenv("PRT_EMUL_F32_LIST") &&
+                    ((sv.h->flags & 8) || std::getenv("PRT_EMUL_F32_ORDERED"));
   prt::f32::SceneViewF sc = {sv.h, sv.comps, sv.leaves, lf.data(), cf.data(), walk ? ordf.data() : nullptr,
                              sv.unboxed};
   long long total = 0;

@@ -186,7 +186,9 @@ def test_fp32_ordered_and_list_walks_agree(monkeypatch):
     cases.append((scene, su.lenslet_rays(centres, 1), 8))
     for scene, rays, gl in cases:
         monkeypatch.delenv("PRT_EMUL_F32_LIST", raising=False)
+        monkeypatch.setenv("PRT_EMUL_F32_ORDERED", "1")
         ordered = emul.trace_f32(scene, rays, gl)
+        monkeypatch.delenv("PRT_EMUL_F32_ORDERED", raising=False)
         monkeypatch.setenv("PRT_EMUL_F32_LIST", "1")
         listed = emul.trace_f32(scene, rays, gl)
         assert np.array_equal(ordered, listed, equal_nan=True)
