@@ -17,7 +17,8 @@
 
 extern "C" {
 cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, int diagnose, cudaStream_t st);
-cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int n_leaves, int n_components, cudaStream_t st);
+cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int ordered, int n_leaves, int n_components,
+                                 cudaStream_t st);
 cudaError_t prt_launch_gather_f32(const prt::GatherArgs* a, cudaStream_t st);
 size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components);
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
@@ -59,6 +60,7 @@ struct prt_scene {
   int n_components = 0;
   std::vector<int> comp_slots;
   int generic = 1;  // some component needs the interpreter for arbitrary CSG trees
+  int ordered = 0;  // the encoder chose the ray-ordered traversal (many boxed components)
   std::vector<unsigned char> staging;  // host copy of the last prt_scene_update (pageable -> the copy is synchronous enough)
 };
 
@@ -105,6 +107,10 @@ int prt_scene_create(const prt_scene_desc* d, int device, prt_scene** out) {
   sc->n_components = d->n_components;
   sc->comp_slots = comp_slots;
   sc->generic = (reinterpret_cast<const prt::BlobHeader*>(blob.data())->flags & 2) ? 1 : 0;
+  {
+    const prt::BlobHeader* bh = reinterpret_cast<const prt::BlobHeader*>(blob.data());
+    sc->ordered = (bh->n_boxed > 0 && (bh->flags & 4) && (bh->flags & 8)) ? 1 : 0;
+  }
   e = cudaMalloc(&sc->d_blob, (size_t)off);
   if (e != cudaSuccess) {
     delete sc;
@@ -148,6 +154,10 @@ int prt_scene_update(prt_scene* sc, const prt_scene_desc* d, void* cuda_stream) 
   sc->n_components = d->n_components;
   sc->comp_slots = comp_slots;
   sc->generic = (reinterpret_cast<const prt::BlobHeader*>(sc->staging.data())->flags & 2) ? 1 : 0;
+  {
+    const prt::BlobHeader* bh = reinterpret_cast<const prt::BlobHeader*>(sc->staging.data());
+    sc->ordered = (bh->n_boxed > 0 && (bh->flags & 4) && (bh->flags & 8)) ? 1 : 0;
+  }
   return PRT_OK;
 }
 
@@ -201,7 +211,7 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
     if (p->flags & PRT_FLAG_DIAGNOSE) return fail(PRT_ERR_UNSUPPORTED, "PRT_FLAG_DIAGNOSE is an FP64 diagnostic");
     if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 52 * 1024)
       return fail(PRT_ERR_LIMIT, "scene too large for the FP32 fast mode's shared-memory staging");
-    cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->n_leaves, scene->n_components,
+    cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->ordered, scene->n_leaves, scene->n_components,
                                            (cudaStream_t)cuda_stream);
     if (e32 != cudaSuccess) return cuda_fail(e32, "trace kernel launch (fp32)");
     return PRT_OK;

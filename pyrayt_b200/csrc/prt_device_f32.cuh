@@ -427,6 +427,9 @@ PRT_HD void eval_comp(const SceneViewF& sc, int c, const RayStateF& r, const Ray
 // visited in the order the ray meets them along its dominant axis, as in the FP64 path (prt_device.cuh,
 // nearest_hit): everything behind the ray is skipped by bisection and the walk stops at the first box that
 // begins beyond the best hit.  Otherwise, and for rays the threshold tests cannot serve, list order.
+// ORDERED = false (the kernel variant for scenes the encoder leaves in list order): a plain loop over the
+// components, nothing else compiled in.
+template <bool ORDERED>
 PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, float& best_t, int& best_leaf,
                         bool& tie) {
   best_t = PRT_INFF;
@@ -440,6 +443,19 @@ PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, f
   const float margin = kCullMarginF * scale;
   const float self_eps = kSelfEps * scale;
   const int nc = sc.h->n_components;
+  if (!ORDERED) {
+    for (int c = 0; c < nc; ++c) {
+      if (c == r.skip) continue;
+      float ct;
+      int cl;
+      eval_comp(sc, c, r, inv, margin, self_eps, best_t, ct, cl, tie);
+      if (ct < best_t) {  // strict: the earlier component keeps a tie (_pyrayt.py:384)
+        best_t = ct;
+        best_leaf = cl;
+      }
+    }
+    return;
+  }
   int best_comp = -1;
   // dominant axis (DomAxis of the FP64 path)
   const float a0 = fabsf(v0), a1 = fabsf(v1), a2 = fabsf(v2);

@@ -40,7 +40,7 @@ __host__ __device__ inline int blob_aligned(int blob_bytes) { return (blob_bytes
 #define PRT_F32_MIN_BLOCKS 4
 #endif
 
-template <bool RECORD>
+template <bool RECORD, bool ORDERED>
 __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f32(const TraceArgs a, int n_leaves, int n_components) {
   extern __shared__ __align__(16) unsigned char s_mem[];
   __shared__ int s_wcount[kTileRays / 32];
@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
   sc.lf = lf;
   sc.cf = cf;
   // ray-ordered traversal for scenes with many boxed components (the encoder's choice, flags bit 3, as on the
-  // FP64 path: config 4 K1 19.5 -> 14.3 ms; small scenes are faster in list order: config 5 25.1 vs 27.7 ms)
-  sc.order = (sc.h->n_boxed > 0 && (sc.h->flags & 4) && (sc.h->flags & 8)) ? ordf : nullptr;
+  // FP64 path: config 4 K1 19.5 -> 14.3 ms; small scenes are faster in list order and run the ORDERED = false
+  // variant, which carries none of the table walk)
+  sc.order = ORDERED ? ordf : nullptr;
   sc.unboxed = reinterpret_cast<const int*>(s_mem + sc.h->off_unboxed);
 
   const long long tile = blockIdx.x;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
       vn = step_speed(rs, ctr);
       if (vn != 0.0f) {
         bool tie = false;
-        nearest_hit(sc, rs, ray_scale(rs), hit_t, hit_leaf, tie);
+        nearest_hit<ORDERED>(sc, rs, ray_scale(rs), hit_t, hit_leaf, tie);
         if (tie) ctr.w1 |= kCtrTie;
       }
     }
@@ -263,19 +264,20 @@ size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components) {
          (size_t)n_components * sizeof(prt::f32::CompF) + (size_t)6 * n_components * sizeof(prt::f32::OrderEntryF);
 }
 
-cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int n_leaves, int n_components,
+// ordered != 0: the scene's header asks for the ray-ordered walk (BlobHeader.flags bits 2 and 3, n_boxed > 0)
+cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int ordered, int n_leaves, int n_components,
                                  cudaStream_t st) {
   const long long tiles = (a->n_rays + prt::kTileRays - 1) / prt::kTileRays;
   if (tiles == 0) return cudaSuccess;
   const size_t smem = prt_f32_smem_bytes(a->blob_bytes, n_leaves, n_components);
-  if (record) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(prt::f32::trace_kernel_f32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prt::f32::trace_kernel_f32<true><<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a, n_leaves, n_components);
+  auto launch = [&](auto kernel) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a, n_leaves, n_components);
+  };
+  if (ordered) {
+    if (record) launch(prt::f32::trace_kernel_f32<true, true>); else launch(prt::f32::trace_kernel_f32<false, true>);
   } else {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(prt::f32::trace_kernel_f32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prt::f32::trace_kernel_f32<false><<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a, n_leaves, n_components);
+    if (record) launch(prt::f32::trace_kernel_f32<true, false>); else launch(prt::f32::trace_kernel_f32<false, false>);
   }
   return cudaGetLastError();
 }

@@ -143,7 +143,8 @@ long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long l
       float t;
       int leaf;
       bool tie = false;
-      prt::f32::nearest_hit(sc, r, prt::f32::ray_scale(r), t, leaf, tie);
+      if (walk) prt::f32::nearest_hit<true>(sc, r, prt::f32::ray_scale(r), t, leaf, tie);
+      else prt::f32::nearest_hit<false>(sc, r, prt::f32::ray_scale(r), t, leaf, tie);
       if (leaf < 0) break;
       if (lf[leaf].mat == PRT_MAT_UNTRACEABLE) break;
       if (total < cap) {

@@ -55,8 +55,8 @@ def test_other_ranks_of_the_reference_arm_stay_silent():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    """profiles/bench_r1_final.json is the line `python bench.py` printed on a B200."""
-    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_r1_final.json")).read().strip().splitlines()[-1])
+    """profiles/bench_r2_final.json is the line `python bench.py` printed on a B200 (round-2 final build)."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "bench_r2_final.json")).read().strip().splitlines()[-1])
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
     assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic" and d["vs_baseline"] is None
     assert d["config"]["workload"] == "config4" and d["config"]["rays_per_gpu"] == 1 << 24
@@ -67,5 +67,18 @@ def test_committed_gpu_line_has_the_contract_keys():
     e2e = d["e2e"]
     assert e2e["h2d_bytes_per_step"] == 13 * 8 * (1 << 24) and e2e["d2h_bytes_per_step"] > 0
     assert e2e["value"] < d["value"]  # host buffers in and out are slower than device-resident steps
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert e2e["host_peak"]["d2h_gbs_aggregate"] > 0 and 0 < e2e["frac_of_host_peak"] <= 1.1
+    # the metric's own baseline: the unmodified NumPy reference timed on the same box, the C port beside it
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] == 1 and cb["value"] > 0
+    assert cb["port"]["kind"] == "port" and cb["port"]["value"] > cb["value"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # the counted exclusions and the optional fast mode
+    nd = d["near_degenerate"]
+    assert nd["rays"] > 0 and nd["grazing_rays"] >= 0 and nd["seam_rays"] >= 0
+    assert d["argsort_mismatch"]["rows_differing"] >= 0
+    f32 = d["fp32_mode"]
+    assert f32["dtype"] == "f32" and f32["value"] > d["value"]
+    ag = f32["agreement_with_fp64"]
+    assert ag["id_columns_equal_on_compared_rows"] and ag["max_error_on_agreeing_rays"] <= 1e-5
+    assert ag["rays_with_different_ids"] + ag["rays_beyond_tolerance"] <= 1e-4 * ag["rays"]
