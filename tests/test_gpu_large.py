@@ -261,6 +261,21 @@ def test_drop_in_raytracer_api(torch_mod):
     tracer.set_generation_limit(1)
     assert tracer.get_rays_per_source() == 5 and tracer.get_generation_limit() == 1
     assert tracer.trace().shape == (5, 15)
+    # extensions of the drop-in: the optional FP32 fast mode and the diagnose counters
+    tracer.set_rays_per_source(21)
+    tracer.set_generation_limit(10)
+    ref = tracer.trace().to_numpy()
+    tracer.precision = "fp32"
+    fast = tracer.trace().to_numpy()
+    assert fast.shape == ref.shape and np.array_equal(fast[:, [0, 4, 5]], ref[:, [0, 4, 5]])
+    assert np.allclose(fast, ref, rtol=0, atol=1e-5 * 4.0)
+    tracer.precision = "fp64"
+    tracer.diagnose = True
+    assert np.array_equal(tracer.trace().to_numpy(), ref)
+    assert tracer.last_result.counters["grazing_rays"] == 0 and tracer.last_result.counters["seam_rays"] == 0
+    tracer.diagnose = False
+    tracer.set_rays_per_source(5)
+    tracer.set_generation_limit(1)
     # a trace with no hit returns the reference's empty float32 frame
     away = su.make_rays([[0, 0, 10.0]], [[0, 0, 1.0]])
     empty = pyrayt_b200.RayTracer(fakes.ArraySource(away), [det], rays_per_source=1).trace()
