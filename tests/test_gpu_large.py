@@ -453,6 +453,55 @@ def test_fp32_fast_mode_on_the_workloads(name, n, max_bad_fraction, torch_mod):
     assert rep["max_error_on_agreeing_rays"] <= 1e-5, rep
 
 
+def test_fp32_fast_mode_full_size_properties(torch_mod):
+    """The FP32 fast mode at the bench size (config 4, 2^24 rays): the size-independent properties of a frame --
+    (generation, id) order, monotone survival, per-ray generation prefixes with no gaps, metadata columns that
+    are copies of the input rays -- and a strided sample against the FP64 oracle within the mode's tolerance."""
+    from oracle import oracle, sources_np
+    from pyrayt_b200 import compare
+
+    torch = torch_mod
+    wl, eng = _engine("config4")
+    n = wl.n_rays
+    d_rays = wl.source.generate(n, device=0)
+    res = eng.trace(d_rays, generation_limit=wl.generation_limit, precision="fp32")
+    f = res.frame
+    assert res.rows == f.shape[1] == res.counters["segments"] and res.counters["rows_dropped"] == 0
+    gen, rid = f[0], f[4]
+    key = gen * float(1 << 26) + rid
+    assert bool((key[1:] > key[:-1]).all())
+    gc = res.gen_counts
+    assert np.all(np.diff(gc) <= 0) and gc.sum() == res.rows
+    ids = rid.to(torch.int64)
+    k = torch.bincount(ids, minlength=n)
+    gs = torch.zeros(n, dtype=torch.float64, device=f.device).index_add_(0, ids, gen)
+    assert bool((gs == (k * (k - 1) / 2).to(torch.float64)).all())
+    # intensity / wavelength are bit-copies of the ray's input values, the surface column holds scene ids
+    assert bool(torch.equal(f[1], d_rays[9][ids])) and bool(torch.equal(f[2], d_rays[10][ids]))
+    sids = torch.from_numpy(wl.scene().leaf_sid.astype(np.float64)).to(f.device)
+    assert bool(torch.isin(f[5], sids).all())
+    # unit tilt columns, hit point = start + distance * tilt direction (single-precision accuracy)
+    nrm = (f[12] ** 2 + f[13] ** 2 + f[14] ** 2).sqrt()
+    assert float((nrm - 1).abs().max()) < 1e-6
+    idx = np.arange(0, n, n // 2048)
+    h = np.hstack([sources_np.from_source(wl.source, 1, first_index=int(i)) for i in idx])
+    want, _ = oracle.trace(wl.scene(), h, wl.generation_limit, threads=THREADS)
+    sel = torch.isin(rid, torch.from_numpy(idx.astype(np.float64)).to(f.device))
+    got = f[:, sel].clone()
+    # renumber the sample's ids 0..2047 so that the agreement helper can index them
+    lut = torch.full((n,), -1, dtype=torch.float64, device=f.device)
+    lut[torch.from_numpy(idx).to(f.device)] = torch.arange(len(idx), dtype=torch.float64, device=f.device)
+    got[4] = lut[got[4].to(torch.int64)]
+    w = torch.from_numpy(want).to(f.device)
+    w[4] = lut[w[4].to(torch.int64)]
+    rep = compare.frame_agreement(w, got, 0, len(idx))
+    assert rep["rays_with_different_ids"] + rep["rays_beyond_tolerance"] <= 2, rep
+    assert rep["id_columns_equal_on_compared_rows"] and rep["max_error_on_agreeing_rays"] <= 1e-5, rep
+    del f, res
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+
+
 def test_lenslet_array_of_973_leaves_is_read_from_global_memory(torch_mod):
     """A 973-leaf scene (18 x 18 lenslets + detector): its encoded form (several hundred KB) does not fit a
     block's shared memory, so the trace kernel reads it in place through L1 / L2 (trace_kernel<.., GLOBAL>).
