@@ -37,7 +37,8 @@
  * prt_intersect / prt_generate_source: they enqueue work on `cuda_stream`
  * (a cudaStream_t passed as void*) and return.
  *
- * All arithmetic is IEEE float64 (the reference computes in float64).
+ * All arithmetic is IEEE float64 without FMA contraction (the reference computes in float64 with NumPy),
+ * except under PRT_FLAG_FP32, the optional single-precision fast mode with a stated tolerance.
  */
 #ifndef PYRAYT_B200_H
 #define PYRAYT_B200_H
