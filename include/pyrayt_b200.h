@@ -169,7 +169,8 @@ typedef struct prt_counters {
   uint64_t segments;           /* rows the trace produced (whether or not capacity allowed the write)  */
   uint64_t rows_reserved;      /* append cursor: staging rows reserved                                 */
   uint64_t rows_dropped;       /* rows not written because staging capacity was exhausted              */
-  uint64_t tie_rays;           /* rays whose CSG merge compared equal finite keys of different leaves  */
+  uint64_t tie_rays;           /* rays whose CSG merge compared equal finite keys of different leaves; the
+                                  closed-form merges of left-deep trees look for them under PRT_FLAG_DIAGNOSE only */
   uint64_t untraceable_hits;   /* nearest hit landed on a PRT_MAT_UNTRACEABLE surface                  */
   uint64_t bad_w;              /* rays whose homogeneous w rows are not (1, 0)                         */
   uint64_t nan_rays;           /* rays terminated because their direction became NaN                   */

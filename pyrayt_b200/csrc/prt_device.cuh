@@ -750,7 +750,8 @@ PRT_HD bool tt_changes(unsigned tt, unsigned before, unsigned own) {
 // (a0,a1), (b0,b1), (c0,c1): sorted hit pairs of leaves A, B, C (+inf = missing entry; LEFT2: c = +inf and
 // tt ignores C).  Returns the nearest positive kept entry (ct, cl) and whether equal keys were compared.
 // (T = double on the FP64 path, float in the FP32 fast mode.)
-template <class T>
+// TIES = false compiles the equal-key detection (a diagnostic counter, prt_counters.tie_rays) out.
+template <bool TIES = true, class T>
 PRT_HD void left_deep_first_hit(unsigned tt, T a0, T a1, T b0, T b1, T c0, T c1, int la, int lb, int lc, T& ct,
                                 int& cl, bool& tie) {
   const T kInf = (T)PRT_INF;
@@ -760,9 +761,10 @@ PRT_HD void left_deep_first_hit(unsigned tt, T a0, T a1, T b0, T b1, T c0, T c1,
   const bool b0a0 = b0 < a0, b1a0 = b1 < a0, b0a1 = b0 < a1, b1a1 = b1 < a1;
   const bool c0a0 = c0 < a0, c1a0 = c1 < a0, c0a1 = c0 < a1, c1a1 = c1 < a1;
   const bool c0b0 = c0 < b0, c1b0 = c1 < b0, c0b1 = c0 < b1, c1b1 = c1 < b1;
-  tie |= (va0 & vb0 & (a0 == b0)) | (va0 & vb1 & (a0 == b1)) | (va1 & vb0 & (a1 == b0)) | (va1 & vb1 & (a1 == b1)) |
-         (va0 & vc0 & (a0 == c0)) | (va0 & vc1 & (a0 == c1)) | (va1 & vc0 & (a1 == c0)) | (va1 & vc1 & (a1 == c1)) |
-         (vb0 & vc0 & (b0 == c0)) | (vb0 & vc1 & (b0 == c1)) | (vb1 & vc0 & (b1 == c0)) | (vb1 & vc1 & (b1 == c1));
+  if (TIES)
+    tie |= (va0 & vb0 & (a0 == b0)) | (va0 & vb1 & (a0 == b1)) | (va1 & vb0 & (a1 == b0)) | (va1 & vb1 & (a1 == b1)) |
+           (va0 & vc0 & (a0 == c0)) | (va0 & vc1 & (a0 == c1)) | (va1 & vc0 & (a1 == c0)) | (va1 & vc1 & (a1 == c1)) |
+           (vb0 & vc0 & (b0 == c0)) | (vb0 & vc1 & (b0 == c1)) | (vb1 & vc0 & (b1 == c0)) | (vb1 & vc1 & (b1 == c1));
   // state of the other leaves just before each entry.  An entry y of a later leaf precedes x only when
   // y < x; an entry y of an earlier leaf precedes x when y <= x, i.e. when !(x < y): in the XOR of a
   // leaf's two entries the two negations cancel, so the same comparison bits serve both directions.
@@ -816,6 +818,7 @@ PRT_HD DomAxis make_dom_axis(double p0, double p1, double p2, double v0, double 
 }
 
 // shapes 2/3: (A op1 B) [op2 C] with their bounding boxes (csg.py:118-160 for a left-deep tree)
+template <bool TIES = true>
 PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double p1, double p2, double v0, double v1,
                            double v2, const RayInv& inv, double best_t, double& ct, int& cl, bool& tie) {
   ct = PRT_INF;
@@ -886,7 +889,7 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
     }
   }
   // a missed inner box empties (A op1 B) whatever the leaves say (csg.py:126-133): a0..q1 are still +inf
-  left_deep_first_hit((unsigned)C.tt, a0, a1, q0, q1, c0, c1, la, lb, lc, ct, cl, tie);
+  left_deep_first_hit<TIES>((unsigned)C.tt, a0, a1, q0, q1, c0, c1, la, lb, lc, ct, cl, tie);
 }
 
 // nearest-hit of _st_propagate over all components (pyrayt/_pyrayt.py:376-386).  The reference visits the
@@ -899,7 +902,9 @@ PRT_HD void eval_left_deep(const SceneView& sc, const Comp& C, double p0, double
 // box are always evaluated; rays the quick tests cannot serve visit every component in list order.
 // GENERIC = false compiles the interpreter for arbitrary trees out: scenes whose components are all
 // bare leaves or left-deep (every reference factory) run a smaller kernel with no lists in memory.
-template <bool GENERIC>
+// TIES = false: the left-deep components do not look for equal merge keys (tie_rays is then only fed by the
+// generic interpreter); the trace kernel counts ties under PRT_FLAG_DIAGNOSE only.
+template <bool GENERIC, bool TIES = true>
 PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, double v0, double v1, double v2,
                         int skip, HitStack* S, double& best_t, int& best_leaf, bool& tie) {
   best_t = PRT_INF;
@@ -954,7 +959,7 @@ PRT_HD void nearest_hit(const SceneView& sc, double p0, double p1, double p2, do
       ct = (t0 > 0) ? t0 : ((t1 > 0) ? t1 : PRT_INF);
       cl = C.leaf_a;
     } else if (shape == SHAPE_LEFT2 || shape == SHAPE_LEFT3) {
-      eval_left_deep(sc, C, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
+      eval_left_deep<TIES>(sc, C, p0, p1, p2, v0, v1, v2, inv, best_t, ct, cl, tie);
     } else if (GENERIC) {
       S->flags = 0;
       if (eval_component(sc, C.begin, C.end, p0, p1, p2, v0, v1, v2, inv, true, best_t, *S, tie)) {

@@ -36,6 +36,11 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 2
 #endif
+#ifdef PRT_TIES_ALWAYS  // experiments: count equal merge keys in every trace, as before round 2's last step
+constexpr bool kTiesAlways = true;
+#else
+constexpr bool kTiesAlways = false;
+#endif
 
 template <bool RECORD, bool GENERIC, bool DIAG = false, bool GLOBAL = false>
 __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
@@ -97,7 +102,8 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) trace_kernel(const 
       vn = step_speed(rs, ctr);
       if (vn != 0.0) {
         bool tie = false;
-        nearest_hit<GENERIC>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, rs.skip, S, hit_t, hit_leaf, tie);
+        // (equal-key detection in the closed-form merges is a diagnostic: compiled in under PRT_FLAG_DIAGNOSE)
+        nearest_hit<GENERIC, DIAG || kTiesAlways>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, rs.skip, S, hit_t, hit_leaf, tie);
         if (tie) ctr.w1 |= kCtrTie;
         if (DIAG)  // PRT_FLAG_DIAGNOSE: four more searches from origins displaced by 1e-9
           ctr.w1 |= diagnose_generation<GENERIC>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, vn, rs.skip, S,

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kWaveTile, PRT_WAVE_MIN_BLOCKS) wave_step_kern
         typename StackFor<GENERIC>::type stack_storage;
         HitStack* S = StackFor<GENERIC>::ptr(stack_storage);
         bool tie = false;
-        nearest_hit<GENERIC>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, rs.skip, S, best_t, leaf, tie);
+        nearest_hit<GENERIC, false>(sc, rs.p0, rs.p1, rs.p2, rs.v0, rs.v1, rs.v2, rs.skip, S, best_t, leaf, tie);
         if (tie && !(flag & kFlagTie)) {
           flag |= kFlagTie;
           n_tie += 1;
