@@ -77,6 +77,16 @@ PRT_HD unsigned exp_of(double x) { return (hi_word(x) >> 20) & 0x7ffu; }
 constexpr unsigned kExpLo = 123;          // 2^-900
 constexpr unsigned kExpSpan = 1923 - 123;  // up to 2^900
 
+// The same window tested on several values at once: the exponent field in place (one mask per value), then
+// integer minimum / maximum (three-input VIMNMX3 on sm_100) and two comparisons for the whole group,
+// instead of a shift, a mask, a subtraction and a comparison per value.
+PRT_HD unsigned mag_of(double x) { return hi_word(x) & 0x7ff00000u; }
+PRT_HD unsigned umin2(unsigned a, unsigned b) { return a < b ? a : b; }
+PRT_HD unsigned umax2(unsigned a, unsigned b) { return a > b ? a : b; }
+PRT_HD bool mags_in_window(unsigned mn, unsigned mx) {
+  return (mn >= (kExpLo << 20)) & (mx < ((kExpLo + kExpSpan) << 20));
+}
+
 PRT_HD Rcp make_rcp(double b) {
   Rcp R;
   R.b = b;
@@ -113,7 +123,8 @@ PRT_HD double div_by(double a, const Rcp& R) {
 PRT_HD void div_by2(double a0, double a1, const Rcp& R, double& q0, double& q1) {
   q0 = div_fast(a0, R);
   q1 = div_fast(a1, R);
-  const bool ok = (exp_of(a0) - kExpLo < R.lim) & (exp_of(a1) - kExpLo < R.lim);
+  const unsigned m0 = mag_of(a0), m1 = mag_of(a1);
+  const bool ok = (R.lim != 0u) & mags_in_window(umin2(m0, m1), umax2(m0, m1));
   if (!ok) {
     q0 = div_by(a0, R);
     q1 = div_by(a1, R);
@@ -123,7 +134,8 @@ PRT_HD void div_by3(double a0, double a1, double a2, const Rcp& R, double& q0, d
   q0 = div_fast(a0, R);
   q1 = div_fast(a1, R);
   q2 = div_fast(a2, R);
-  const bool ok = (exp_of(a0) - kExpLo < R.lim) & (exp_of(a1) - kExpLo < R.lim) & (exp_of(a2) - kExpLo < R.lim);
+  const unsigned m0 = mag_of(a0), m1 = mag_of(a1), m2 = mag_of(a2);
+  const bool ok = (R.lim != 0u) & mags_in_window(umin2(umin2(m0, m1), m2), umax2(umax2(m0, m1), m2));
   if (!ok) {
     q0 = div_by(a0, R);
     q1 = div_by(a1, R);
@@ -492,10 +504,11 @@ PRT_HD bool lens3_hits_fast(const Leaf& Y, const Leaf& A, const Leaf& B, double 
   b0 = div_fast(bn0, bden);
   b1 = div_fast(bn1, bden);
   double c0 = div_fast(zn0, zden), c1 = div_fast(zn1, zden);
-  const bool ok = (exp_of(yn0) - kExpLo < yden.lim) & (exp_of(yn1) - kExpLo < yden.lim) &
-                  (exp_of(an0) - kExpLo < aden.lim) & (exp_of(an1) - kExpLo < aden.lim) &
-                  (exp_of(bn0) - kExpLo < bden.lim) & (exp_of(bn1) - kExpLo < bden.lim) &
-                  (exp_of(zn0) - kExpLo < zden.lim) & (exp_of(zn1) - kExpLo < zden.lim);
+  const unsigned my0 = mag_of(yn0), my1 = mag_of(yn1), ma0 = mag_of(an0), ma1 = mag_of(an1);
+  const unsigned mb0 = mag_of(bn0), mb1 = mag_of(bn1), mz0 = mag_of(zn0), mz1 = mag_of(zn1);
+  const unsigned mn = umin2(umin2(umin2(my0, my1), umin2(ma0, ma1)), umin2(umin2(mb0, mb1), umin2(mz0, mz1)));
+  const unsigned mx = umax2(umax2(umax2(my0, my1), umax2(ma0, ma1)), umax2(umax2(mb0, mb1), umax2(mz0, mz1)));
+  const bool ok = ((yden.lim != 0u) & (aden.lim != 0u) & (bden.lim != 0u) & (zden.lim != 0u)) & mags_in_window(mn, mx);
   if (!(ydisc >= 0)) {
     s0 = PRT_INF;
     s1 = PRT_INF;

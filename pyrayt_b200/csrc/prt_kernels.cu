@@ -280,8 +280,14 @@ __global__ void gen_offsets_kernel(long long* gen_offsets, int generation_limit)
 // (_RayTraceDataframe.insert, pyrayt/_pyrayt.py:168-186: current metadata, surface id, start point, end
 // point = start + direction * distance (:404-407), unit tilt (:177)).  Same functions and the same
 // -fmad=false arithmetic as the trace kernel, so the columns are bit-identical to computing them there.
+// Four blocks per SM (64 registers; 28 bytes of spills): at the 72 registers the compiler takes unasked the
+// pass loses a quarter of its warps and 0.9 ms; five blocks (48 registers) and plain IEEE divisions in place of
+// unit_tilt were measured too (config 4 step 45.9 / 45.2 ms against 44.9; profiles/r2/kbench_r2o.txt).
+#ifndef PRT_GATHER_BLOCKS
+#define PRT_GATHER_BLOCKS 4
+#endif
 template <int LAYOUT>
-__global__ void __launch_bounds__(kTileRays) gather_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(kTileRays, PRT_GATHER_BLOCKS) gather_kernel(const GatherArgs a) {
   const long long tile = blockIdx.x;
   const Leaf* leaves =
       reinterpret_cast<const Leaf*>(a.blob + reinterpret_cast<const BlobHeader*>(a.blob)->off_leaves);
@@ -293,6 +299,8 @@ __global__ void __launch_bounds__(kTileRays) gather_kernel(const GatherArgs a) {
       const long long src = a.run_start[idx] + threadIdx.x;
       const long long dst = a.gen_offsets[g] + a.run_base[idx] + threadIdx.x;
       if (dst >= a.frame_capacity) continue;
+      // all loads first (memory-level parallelism: a version that stored each column as soon as it was known
+      // was 1.5 ms slower), then the fifteen stores
       double s[kStageCols];
 #pragma unroll
       for (int k = 0; k < kStageCols; ++k) s[k] = __ldcs(a.stage + k * a.capacity + src);
