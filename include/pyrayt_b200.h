@@ -61,8 +61,8 @@ extern "C" {
 #define PRT_MAX_SLOTS 32
 /* largest scene a handle accepts.  Scenes whose encoded form fits a thread block's share of shared memory
  * (about 100 KB: a few hundred leaves) are staged there by every block; larger ones (lenslet arrays, ...) are
- * read through L1 / L2 by prt_trace (prt_intersect, prt_nearest_hit, prt_render_hit, prt_trace_wavefront and
- * the FP32 fast mode return PRT_ERR_LIMIT for them) */
+ * read in place through L1 / L2 by prt_trace, prt_intersect, prt_nearest_hit and prt_render_hit
+ * (prt_trace_wavefront and the FP32 fast mode return PRT_ERR_LIMIT for them) */
 #define PRT_MAX_LEAVES 4096
 #define PRT_MAX_NODES 8192
 

@@ -328,7 +328,6 @@ int prt_intersect(prt_scene* scene, int32_t component, const double* d_rays, int
   if (slots_out) *slots_out = slots;
   if (n == 0) return PRT_OK;
   if (!d_rays || !d_hits || !d_sids) return fail(PRT_ERR_INVALID, "null buffer");
-  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   cudaError_t e = prt_launch_intersect(scene->d_blob, scene->blob_bytes, component, d_rays, n, d_hits,
                                        reinterpret_cast<long long*>(d_sids), slots, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "intersect kernel launch");
@@ -341,7 +340,6 @@ int prt_nearest_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d
   if (n < 0) return fail(PRT_ERR_INVALID, "negative ray count");
   if (n == 0) return PRT_OK;
   if (!d_rays || !d_t || !d_sid) return fail(PRT_ERR_INVALID, "null buffer");
-  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   cudaError_t e = prt_launch_nearest(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
                                      reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "nearest kernel launch");
@@ -354,7 +352,6 @@ int prt_render_hit(prt_scene* scene, const double* d_rays, int64_t n, double* d_
   if (n < 0) return fail(PRT_ERR_INVALID, "negative ray count");
   if (n == 0) return PRT_OK;
   if (!d_rays || !d_t || !d_sid) return fail(PRT_ERR_INVALID, "null buffer");
-  if (scene->blob_bytes > prt::kMaxSharedBlob) return fail(PRT_ERR_LIMIT, "scene too large for this entry point (prt_trace reads large scenes from global memory)");
   cudaError_t e = prt_launch_render_hit(scene->d_blob, scene->blob_bytes, d_rays, n, d_t,
                                         reinterpret_cast<long long*>(d_sid), d_normals, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "render hit kernel launch");

@@ -335,18 +335,19 @@ __global__ void __launch_bounds__(kTileRays, PRT_GATHER_BLOCKS) gather_kernel(co
 
 // ---------------------------------------------------------------- component.intersect
 
+template <bool GLOBAL>
 __global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned char* blob, int blob_bytes,
                                                               int component, const double* rays, long long n,
                                                               double* hits, long long* sids, int slots) {
   extern __shared__ __align__(16) unsigned char s_blob[];
-  {
+  if (!GLOBAL) {  // (GLOBAL: a scene too large for shared memory is read in place, through L1 / L2)
     const int words = blob_bytes / 8;
     const double* src = reinterpret_cast<const double*>(blob);
     double* dst = reinterpret_cast<double*>(s_blob);
     for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
   }
   __syncthreads();
-  const SceneView sc = make_view(s_blob);
+  const SceneView sc = make_view(GLOBAL ? blob : s_blob);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
@@ -365,18 +366,19 @@ __global__ void __launch_bounds__(kTileRays) intersect_kernel(const unsigned cha
 
 // ---------------------------------------------------------------- _st_propagate alone (renderers, probes)
 
+template <bool GLOBAL>
 __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) nearest_kernel(const unsigned char* blob, int blob_bytes,
                                                                            const double* rays, long long n, double* t_out,
                                                                            long long* sid_out, double* normals) {
   extern __shared__ __align__(16) unsigned char s_blob[];
-  {
+  if (!GLOBAL) {  // (GLOBAL: a scene too large for shared memory is read in place, through L1 / L2)
     const int words = blob_bytes / 8;
     const double* src = reinterpret_cast<const double*>(blob);
     double* dst = reinterpret_cast<double*>(s_blob);
     for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
   }
   __syncthreads();
-  const SceneView sc = make_view(s_blob);
+  const SceneView sc = make_view(GLOBAL ? blob : s_blob);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
@@ -402,18 +404,19 @@ __global__ void __launch_bounds__(kTileRays, PRT_MIN_BLOCKS) nearest_kernel(cons
 // except that the distance and surface are read from the *unfiltered* hit array at the argmin of the
 // filtered one -- a pixel whose component hits are all behind the camera reports slot 0, a negative
 // distance.  Needs every hit of every component, so it runs the interpreter without pruning.
+template <bool GLOBAL>
 __global__ void __launch_bounds__(kTileRays) render_hit_kernel(const unsigned char* blob, int blob_bytes,
                                                                const double* rays, long long n, double* t_out,
                                                                long long* sid_out, double* normals) {
   extern __shared__ __align__(16) unsigned char s_blob[];
-  {
+  if (!GLOBAL) {  // (GLOBAL: a scene too large for shared memory is read in place, through L1 / L2)
     const int words = blob_bytes / 8;
     const double* src = reinterpret_cast<const double*>(blob);
     double* dst = reinterpret_cast<double*>(s_blob);
     for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
   }
   __syncthreads();
-  const SceneView sc = make_view(s_blob);
+  const SceneView sc = make_view(GLOBAL ? blob : s_blob);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double p0 = rays[0 * n + i], p1 = rays[1 * n + i], p2 = rays[2 * n + i];
@@ -719,10 +722,15 @@ cudaError_t prt_launch_intersect(const unsigned char* blob, int blob_bytes, int 
                                  long long n, double* hits, long long* sids, int slots, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + prt::kTileRays - 1) / prt::kTileRays);
+  if (blob_bytes > prt::kMaxSharedBlob) {
+    prt::intersect_kernel<true><<<blocks, prt::kTileRays, 0, st>>>(blob, blob_bytes, component, rays, n, hits, sids,
+                                                                   slots);
+    return cudaGetLastError();
+  }
   if (blob_bytes > 48 * 1024)
-    cudaFuncSetAttribute(prt::intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
-  prt::intersect_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, component, rays, n,
-                                                                            hits, sids, slots);
+    cudaFuncSetAttribute(prt::intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
+  prt::intersect_kernel<false><<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, component, rays,
+                                                                                   n, hits, sids, slots);
   return cudaGetLastError();
 }
 
@@ -730,10 +738,14 @@ cudaError_t prt_launch_nearest(const unsigned char* blob, int blob_bytes, const 
                                long long* sid_out, double* normals, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + prt::kTileRays - 1) / prt::kTileRays);
+  if (blob_bytes > prt::kMaxSharedBlob) {
+    prt::nearest_kernel<true><<<blocks, prt::kTileRays, 0, st>>>(blob, blob_bytes, rays, n, t_out, sid_out, normals);
+    return cudaGetLastError();
+  }
   if (blob_bytes > 48 * 1024)
-    cudaFuncSetAttribute(prt::nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
-  prt::nearest_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out, sid_out,
-                                                                          normals);
+    cudaFuncSetAttribute(prt::nearest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
+  prt::nearest_kernel<false><<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out,
+                                                                                 sid_out, normals);
   return cudaGetLastError();
 }
 
@@ -741,10 +753,15 @@ cudaError_t prt_launch_render_hit(const unsigned char* blob, int blob_bytes, con
                                   double* t_out, long long* sid_out, double* normals, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + prt::kTileRays - 1) / prt::kTileRays);
+  if (blob_bytes > prt::kMaxSharedBlob) {
+    prt::render_hit_kernel<true><<<blocks, prt::kTileRays, 0, st>>>(blob, blob_bytes, rays, n, t_out, sid_out,
+                                                                    normals);
+    return cudaGetLastError();
+  }
   if (blob_bytes > 48 * 1024)
-    cudaFuncSetAttribute(prt::render_hit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
-  prt::render_hit_kernel<<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out, sid_out,
-                                                                            normals);
+    cudaFuncSetAttribute(prt::render_hit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, blob_bytes);
+  prt::render_hit_kernel<false><<<blocks, prt::kTileRays, (size_t)blob_bytes, st>>>(blob, blob_bytes, rays, n, t_out,
+                                                                                    sid_out, normals);
   return cudaGetLastError();
 }
 

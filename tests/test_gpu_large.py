@@ -505,8 +505,9 @@ def test_fp32_fast_mode_full_size_properties(torch_mod):
 def test_lenslet_array_of_973_leaves_is_read_from_global_memory(torch_mod):
     """A 973-leaf scene (18 x 18 lenslets + detector): its encoded form (several hundred KB) does not fit a
     block's shared memory, so the trace kernel reads it in place through L1 / L2 (trace_kernel<.., GLOBAL>).
-    Frame bit-equal to the oracle, counters-only and diagnosing traces agree, the entry points that only stage
-    in shared memory refuse it with PRT_ERR_LIMIT."""
+    Frame bit-equal to the oracle, counters-only and diagnosing traces agree, component.intersect and the
+    nearest / render hits read it in place too; the FP32 mode and the wavefront driver (shared memory only)
+    refuse it with PRT_ERR_LIMIT."""
     import pyrayt_b200
     from oracle import oracle
     from tests import scene_util as su
@@ -526,8 +527,17 @@ def test_lenslet_array_of_973_leaves_is_read_from_global_memory(torch_mod):
     diag = eng.trace(torch.from_numpy(sub).cuda(), generation_limit=8, diagnose=True)
     o = oracle.diagnose(scene, sub, 8, threads=THREADS)
     assert (diag.counters["grazing_rays"], diag.counters["seam_rays"]) == (o["grazing_rays"], o["seam_rays"])
-    with pytest.raises(pyrayt_b200.PrtError, match="too large"):
-        eng.nearest_hit(torch.zeros((2, 4, 8), dtype=torch.float64, device="cuda"))
+    # the plugin entry points read the large scene in place too: component.intersect, nearest / render hits
+    r8 = np.zeros((8, 512))
+    r8[0:3], r8[3], r8[4:7] = rays[0:3, :512], 1, rays[4:7, :512]
+    for renderer in (False, True):
+        t, s, nrm = eng.nearest_hit(torch.from_numpy(r8).cuda(), normals=True, renderer=renderer)
+        ot, osid, onrm = (oracle.render_hit if renderer else oracle.nearest)(scene, r8)
+        assert np.array_equal(t.cpu().numpy(), ot) and np.array_equal(s.cpu().numpy(), osid)
+    for c in (0, 161, 324):
+        hits, sids = eng.intersect(c, torch.from_numpy(r8.reshape(2, 4, -1)).cuda())
+        oh, os_ = oracle.intersect(scene, c, r8.reshape(2, 4, -1))
+        assert np.array_equal(hits.cpu().numpy(), oh, equal_nan=True) and np.array_equal(sids.cpu().numpy(), os_)
     with pytest.raises(pyrayt_b200.PrtError, match="too large"):
         eng.trace(d, generation_limit=8, precision="fp32")
     with pytest.raises(pyrayt_b200.PrtError, match="too large"):
