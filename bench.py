@@ -447,7 +447,10 @@ def main():
     # ------------------------------------------------------------------ the optional FP32 fast mode (north star)
     fp32 = None
     if not args.no_fp32 and not scene_needs_interpreter(scene):
-        fp32 = run_fp32_mode(torch, engine, d_rays, n, n_total, G, args.steps, ev, barrier, max_over_ranks)
+        try:
+            fp32 = run_fp32_mode(torch, engine, d_rays, n, n_total, G, args.steps, ev, barrier, max_over_ranks)
+        except _lib.PrtError as exc:  # the library is the judge of what the mode supports; never fail the bench for it
+            fp32 = {"unsupported": str(exc)}
         torch.cuda.empty_cache()
     if not args.no_e2e:
         e2e = run_e2e(args, torch, engine, d_rays, n, n_total, G, rows, world, barrier, max_over_ranks)
