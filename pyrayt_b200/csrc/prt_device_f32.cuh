@@ -101,7 +101,6 @@ PRT_HD void convert_comp(const Comp& C, CompF& F) {
 }
 
 PRT_HD bool isz(float x) { return fabsf(x) <= 1e-8f; }
-PRT_HD bool iscl(float p, float v) { return (fabsf(p - v) <= (1e-8f + 1e-5f * fabsf(v))) | (p == v); }
 PRT_HD void sort2(float& a, float& b) {
   const float lo = fminf(a, b), hi = fmaxf(a, b);
   // fmin / fmax drop NaNs; hit parameters here are never NaN unless the ray is (dead anyway)
@@ -378,10 +377,9 @@ struct RayStateF {
   int self;  // leaf the ray has just interacted with, or -1
 };
 
-// one component for nearest_hit: its first positive kept entry (ct, cl), or ct = +inf.  `boxed`: the caller has
-// already dealt with the component's root box (ray-ordered walk); otherwise components with a proven /
-// conservative box (Comp.flags & 5) are skipped when the box lies behind the ray or beyond the best hit so far.
-// A CSG component whose root box the ray misses has no hits either way (csg.py:126-133).
+// one component for nearest_hit: its first positive kept entry (ct, cl), or ct = +inf.  Components with a proven /
+// conservative box (Comp.flags & 5) are skipped when the box lies behind the ray or beyond the best hit so far;
+// a CSG component whose root box the ray misses has no hits at all (csg.py:126-133).
 PRT_HD void eval_comp(const SceneViewF& sc, int c, const RayStateF& r, const RayInvF& inv, float margin,
                       float self_eps, float best_t, float& ct, int& cl, bool& tie) {
   const float p0 = r.p0, p1 = r.p1, p2 = r.p2, v0 = r.v0, v1 = r.v1, v2 = r.v2;
