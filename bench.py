@@ -446,7 +446,7 @@ def main():
     torch.cuda.empty_cache()
     # ------------------------------------------------------------------ the optional FP32 fast mode (north star)
     fp32 = None
-    if not args.no_fp32 and not scene_needs_interpreter(scene):
+    if not args.no_fp32:
         try:
             fp32 = run_fp32_mode(torch, engine, d_rays, n, n_total, G, args.steps, ev, barrier, max_over_ranks)
         except _lib.PrtError as exc:  # the library is the judge of what the mode supports; never fail the bench for it
@@ -495,19 +495,6 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def scene_needs_interpreter(scene):
-    """True when some component is not a bare surface or a left-deep tree of <= 3 leaves (FP32 mode: unsupported)."""
-    import numpy as np
-
-    for c in range(scene.n_components):
-        kinds = scene.node_kind[scene.comp_node_begin[c]: scene.comp_node_begin[c + 1]]
-        n = len(kinds)
-        ok = (n == 1) or (n == 3 and list(kinds[:2]) == [0, 0]) or (n == 5 and list(kinds[:2]) == [0, 0] and kinds[3] == 0)
-        if not ok:
-            return True
-    return False
 
 
 def run_fp32_mode(torch, engine, d_rays, n, n_total, G, steps, ev, barrier, max_over_ranks):

@@ -17,10 +17,10 @@
 
 extern "C" {
 cudaError_t prt_launch_trace(const prt::TraceArgs* a, int record, int generic, int diagnose, cudaStream_t st);
-cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int ordered, int n_leaves, int n_components,
-                                 cudaStream_t st);
+cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int ordered, int generic, int n_leaves,
+                                 int n_components, int n_aabb, cudaStream_t st);
 cudaError_t prt_launch_gather_f32(const prt::GatherArgs* a, cudaStream_t st);
-size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components);
+size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components, int n_aabb);
 cudaError_t prt_launch_scan(const int* run_count, long long* run_base, long long n_tiles, int generation_limit,
                             long long* gen_offsets, cudaStream_t st);
 cudaError_t prt_launch_gather(const prt::GatherArgs* a, int layout, cudaStream_t st);
@@ -61,6 +61,7 @@ struct prt_scene {
   std::vector<int> comp_slots;
   int generic = 1;  // some component needs the interpreter for arbitrary CSG trees
   int ordered = 0;  // the encoder chose the ray-ordered traversal (many boxed components)
+  int n_aabb = 0;   // node boxes of the interpreter's programs
   std::vector<unsigned char> staging;  // host copy of the last prt_scene_update (pageable -> the copy is synchronous enough)
 };
 
@@ -110,6 +111,7 @@ int prt_scene_create(const prt_scene_desc* d, int device, prt_scene** out) {
   {
     const prt::BlobHeader* bh = reinterpret_cast<const prt::BlobHeader*>(blob.data());
     sc->ordered = (bh->n_boxed > 0 && (bh->flags & 4) && (bh->flags & 8)) ? 1 : 0;
+    sc->n_aabb = bh->n_aabb;
   }
   e = cudaMalloc(&sc->d_blob, (size_t)off);
   if (e != cudaSuccess) {
@@ -157,6 +159,7 @@ int prt_scene_update(prt_scene* sc, const prt_scene_desc* d, void* cuda_stream) 
   {
     const prt::BlobHeader* bh = reinterpret_cast<const prt::BlobHeader*>(sc->staging.data());
     sc->ordered = (bh->n_boxed > 0 && (bh->flags & 4) && (bh->flags & 8)) ? 1 : 0;
+    sc->n_aabb = bh->n_aabb;
   }
   return PRT_OK;
 }
@@ -205,14 +208,11 @@ int prt_trace(prt_scene* scene, const prt_params* p, const double* d_rays, int64
   a.stride = ray_stride;
   a.ctr = d_counters;
   if (p->flags & PRT_FLAG_FP32) {
-    if (scene->generic)
-      return fail(PRT_ERR_UNSUPPORTED, "the FP32 fast mode traces bare surfaces and left-deep CSG trees of up to three "
-                                       "leaves (everything the reference's factories build); this scene needs FP64");
     if (p->flags & PRT_FLAG_DIAGNOSE) return fail(PRT_ERR_UNSUPPORTED, "PRT_FLAG_DIAGNOSE is an FP64 diagnostic");
-    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components) > 52 * 1024)
+    if (prt_f32_smem_bytes(scene->blob_bytes, scene->n_leaves, scene->n_components, scene->n_aabb) > 52 * 1024)
       return fail(PRT_ERR_LIMIT, "scene too large for the FP32 fast mode's shared-memory staging");
-    cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->ordered, scene->n_leaves, scene->n_components,
-                                           (cudaStream_t)cuda_stream);
+    cudaError_t e32 = prt_launch_trace_f32(&a, record ? 1 : 0, scene->ordered, scene->generic, scene->n_leaves,
+                                           scene->n_components, scene->n_aabb, (cudaStream_t)cuda_stream);
     if (e32 != cudaSuccess) return cuda_fail(e32, "trace kernel launch (fp32)");
     return PRT_OK;
   }

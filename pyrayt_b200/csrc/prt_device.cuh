@@ -617,20 +617,23 @@ PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double&
 // list is represented by its prefix of entries < +inf.  Parity is by *index in the child
 // list* exactly as in csg.py:41,:46.
 
-struct HitStack {
-  double t[kMaxDepth * 2][kMaxSlots];
+template <class T>  // T = double (FP64 path) or float (FP32 fast mode)
+struct HitStackT {
+  typedef T value_type;
+  T t[kMaxDepth * 2][kMaxSlots];
   unsigned short leaf[kMaxDepth * 2][kMaxSlots];
   int len[kMaxDepth];
   unsigned flags;  // bit s: which of the two buffers of level s is live
 };
+typedef HitStackT<double> HitStack;
 
-PRT_HD int buf_of(const HitStack& S, int lvl) { return lvl * 2 + ((S.flags >> lvl) & 1); }
+template <class Stack>
+PRT_HD int buf_of(const Stack& S, int lvl) { return lvl * 2 + ((S.flags >> lvl) & 1); }
 
 // streaming form of array_csg (csg.py:13-61) + the two argsorts of CSGSurface.intersect (:138-149):
 // L = live buffer of level `lvl`; R = (r_t, r_leaf, nR) supplied by get_r; result replaces L.
-template <class GetRT, class GetRL>
-PRT_HD void merge_lists(HitStack& S, int lvl, int op, int nR, GetRT r_t, GetRL r_leaf,
-                                            bool& tie) {
+template <class Stack, class GetRT, class GetRL>
+PRT_HD void merge_lists(Stack& S, int lvl, int op, int nR, GetRT r_t, GetRL r_leaf, bool& tie) {
   const int src = buf_of(S, lvl);
   const int dst = src ^ 1;
   const int nL = S.len[lvl];
@@ -640,7 +643,7 @@ PRT_HD void merge_lists(HitStack& S, int lvl, int op, int nR, GetRT r_t, GetRL r
   const int rflip = (op == PRT_DIFFERENCE) ? 1 : 0;
   while (i < nL || j < nR) {
     bool takeL;
-    double tl = 0, tr = 0;
+    typename Stack::value_type tl = 0, tr = 0;
     if (j >= nR) {
       takeL = true;
       tl = S.t[src][i];

@@ -1,7 +1,8 @@
 // Per-ray device functions of the optional FP32 fast mode (PRT_FLAG_FP32, include/pyrayt_b200.h).
 //
 // The same path as prt_device.cuh -- world->object transform, primitive intersect (primitives.py:241-741),
-// CSG merge of the left-deep trees the reference's factories build (csg.py:13-160), nearest hit
+// CSG merge (csg.py:13-160: closed form for the left-deep trees the reference's factories build, the streaming
+// interpreter of prt_device.cuh for any other tree), nearest hit
 // (_pyrayt.py:370-392), normals and material interaction (world_objects.py:401-418, operations.py:86-162,
 // materials.py:47-145) -- in single precision, with FMA contraction and the fast division / square root.
 // Contract: the frame agrees with the FP64 frame to the tolerance stated in DESIGN.md (1e-5 of the scene
@@ -56,7 +57,11 @@ struct SceneViewF {
   const CompF* cf;
   const OrderEntryF* order;  // [6][n_boxed] ray-ordered traversal tables, or nullptr (list-order walk)
   const int* unboxed;        // [n_unboxed]
+  const Op* ops;             // preorder programs of the components that need the interpreter
+  const float* aabb;         // [n_aabb][6] their node boxes, rounded outwards (nullptr: no such component)
 };
+
+typedef HitStackT<float> HitStackF;
 
 // double -> float, rounded down / up (boxes are rounded outwards so that a single-precision box still
 // contains the FP64 one)
@@ -377,11 +382,62 @@ struct RayStateF {
   int self;  // leaf the ray has just interacted with, or -1
 };
 
+// component.intersect for one ray by the preorder interpreter (eval_component of prt_device.cuh in single
+// precision): any CSG tree.  Returns false when the root box is missed or, for proven boxes, lies behind the ray or
+// beyond the best hit so far.
+PRT_HD bool eval_component(const SceneViewF& sc, int begin, int end, const RayStateF& r, const RayInvF& inv,
+                           float margin, float self_eps, float best_t, HitStackF& S, bool& tie) {
+  const float p0 = r.p0, p1 = r.p1, p2 = r.p2, v0 = r.v0, v1 = r.v1, v2 = r.v2;
+  int sp = 0;
+  int pc = begin;
+  while (pc < end) {
+    const Op op = sc.ops[pc];
+    if (op.kind == OP_ENTER) {
+      float b0, b1;
+      box_hits(sc.aabb + 6 * op.a, p0, p1, p2, v0, v1, v2, inv, b0, b1);
+      if (!(b0 < PRT_INFF)) {  // csg.py:126-133
+        if (pc == begin) return false;
+        S.len[sp++] = 0;
+        pc = op.b;
+        continue;
+      }
+      if (pc == begin && (op.c & 1) && (b1 < -margin || b0 > best_t + margin)) return false;
+    } else if (op.kind == OP_LEAF) {
+      float t0, t1;
+      leaf_hits(sc.lf[op.a], p0, p1, p2, v0, v1, v2, (op.a == r.self) ? self_eps : 0.0f, t0, t1);
+      const int b = buf_of(S, sp);
+      S.t[b][0] = t0;
+      S.t[b][1] = t1;
+      S.leaf[b][0] = (unsigned short)op.a;
+      S.leaf[b][1] = (unsigned short)op.a;
+      S.len[sp++] = (t0 < PRT_INFF) ? ((t1 < PRT_INFF) ? 2 : 1) : 0;
+    } else if (op.kind == OP_MERGE_LEAF) {
+      float t0, t1;
+      leaf_hits(sc.lf[op.b], p0, p1, p2, v0, v1, v2, (op.b == r.self) ? self_eps : 0.0f, t0, t1);
+      const int n = (t0 < PRT_INFF) ? ((t1 < PRT_INFF) ? 2 : 1) : 0;
+      const int lf = op.b;
+      merge_lists(
+          S, sp - 1, op.a, n, [&](int j) { return j ? t1 : t0; }, [&](int) { return lf; }, tie);
+    } else {  // OP_MERGE
+      const int rl = sp - 1;
+      const int rb = buf_of(S, rl);
+      merge_lists(
+          S, sp - 2, op.a, S.len[rl], [&](int j) { return S.t[rb][j]; }, [&](int j) { return (int)S.leaf[rb][j]; },
+          tie);
+      --sp;
+    }
+    ++pc;
+  }
+  return true;
+}
+
 // one component for nearest_hit: its first positive kept entry (ct, cl), or ct = +inf.  Components with a proven /
 // conservative box (Comp.flags & 5) are skipped when the box lies behind the ray or beyond the best hit so far;
 // a CSG component whose root box the ray misses has no hits at all (csg.py:126-133).
+// GENERIC = false compiles the interpreter out (scenes of bare surfaces and left-deep trees).
+template <bool GENERIC>
 PRT_HD void eval_comp(const SceneViewF& sc, int c, const RayStateF& r, const RayInvF& inv, float margin,
-                      float self_eps, float best_t, float& ct, int& cl, bool& tie) {
+                      float self_eps, float best_t, HitStackF* S, float& ct, int& cl, bool& tie) {
   const float p0 = r.p0, p1 = r.p1, p2 = r.p2, v0 = r.v0, v1 = r.v1, v2 = r.v2;
   const Comp& C = sc.comps[c];
   const CompF& F = sc.cf[c];
@@ -400,7 +456,25 @@ PRT_HD void eval_comp(const SceneViewF& sc, int c, const RayStateF& r, const Ray
     cl = C.leaf_a;
     return;
   }
-  // SHAPE_LEFT2 / SHAPE_LEFT3 (the ABI refuses other trees in this mode)
+  if (shape == SHAPE_GENERIC) {
+    if (GENERIC) {
+      S->flags = 0;
+      if (eval_component(sc, C.begin, C.end, r, inv, margin, self_eps, best_t, *S, tie)) {
+        const int b = buf_of(*S, 0);
+        const int n = S->len[0];
+        for (int q = 0; q < n; ++q) {  // sorted: the first positive entry is the argmin of where(hits > 0)
+          const float t = S->t[b][q];
+          if (t > 0) {
+            ct = t;
+            cl = S->leaf[b][q];
+            break;
+          }
+        }
+      }
+    }
+    return;
+  }
+  // SHAPE_LEFT2 / SHAPE_LEFT3
   float b0, b1;
   box_hits(F.root_box, p0, p1, p2, v0, v1, v2, inv, b0, b1);
   if (!(b0 < PRT_INFF)) return;
@@ -427,9 +501,9 @@ PRT_HD void eval_comp(const SceneViewF& sc, int c, const RayStateF& r, const Ray
 // begins beyond the best hit.  Otherwise, and for rays the threshold tests cannot serve, list order.
 // ORDERED = false (the kernel variant for scenes the encoder leaves in list order): a plain loop over the
 // components, nothing else compiled in.
-template <bool ORDERED>
-PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, float& best_t, int& best_leaf,
-                        bool& tie) {
+template <bool ORDERED, bool GENERIC>
+PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, HitStackF* S, float& best_t,
+                        int& best_leaf, bool& tie) {
   best_t = PRT_INFF;
   best_leaf = -1;
   const float v0 = r.v0, v1 = r.v1, v2 = r.v2;
@@ -446,7 +520,7 @@ PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, f
       if (c == r.skip) continue;
       float ct;
       int cl;
-      eval_comp(sc, c, r, inv, margin, self_eps, best_t, ct, cl, tie);
+      eval_comp<GENERIC>(sc, c, r, inv, margin, self_eps, best_t, S, ct, cl, tie);
       if (ct < best_t) {  // strict: the earlier component keeps a tie (_pyrayt.py:384)
         best_t = ct;
         best_leaf = cl;
@@ -499,7 +573,7 @@ PRT_HD void nearest_hit(const SceneViewF& sc, const RayStateF& r, float scale, f
     if (c == r.skip) continue;
     float ct;
     int cl;
-    eval_comp(sc, c, r, inv, margin, self_eps, best_t, ct, cl, tie);
+    eval_comp<GENERIC>(sc, c, r, inv, margin, self_eps, best_t, S, ct, cl, tie);
     // smallest distance, then earliest component (== the reference's in-order strict `<`, _pyrayt.py:384)
     if ((ct < best_t) | ((ct == best_t) & (ct < PRT_INFF) & (c < best_comp))) {
       best_t = ct;

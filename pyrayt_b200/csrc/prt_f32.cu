@@ -33,14 +33,26 @@ __device__ __forceinline__ void unpack2(double w, float& a, float& b) {
   b = __uint_as_float((unsigned)(u >> 32));
 }
 
-// bytes of dynamic shared memory: the FP64 blob, then LeafF[n_leaves], CompF[n_components], OrderEntryF[6][n_boxed]
+// bytes of dynamic shared memory: the FP64 blob, then LeafF[n_leaves], CompF[n_components],
+// OrderEntryF[6][n_components] and float[6][n_aabb]
 __host__ __device__ inline int blob_aligned(int blob_bytes) { return (blob_bytes + 15) & ~15; }
+
+template <bool GENERIC>
+struct StackForF {
+  typedef HitStackF type;
+  __device__ static HitStackF* ptr(HitStackF& s) { return &s; }
+};
+template <>
+struct StackForF<false> {
+  typedef char type;
+  __device__ static HitStackF* ptr(char&) { return nullptr; }
+};
 
 #ifndef PRT_F32_MIN_BLOCKS
 #define PRT_F32_MIN_BLOCKS 4
 #endif
 
-template <bool RECORD, bool ORDERED>
+template <bool RECORD, bool ORDERED, bool GENERIC>
 __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f32(const TraceArgs a, int n_leaves, int n_components) {
   extern __shared__ __align__(16) unsigned char s_mem[];
   __shared__ int s_wcount[kTileRays / 32];
@@ -58,10 +70,16 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
   LeafF* lf = reinterpret_cast<LeafF*>(s_mem + blob_aligned(a.blob_bytes));
   CompF* cf = reinterpret_cast<CompF*>(lf + n_leaves);
   OrderEntryF* ordf = reinterpret_cast<OrderEntryF*>(cf + n_components);
+  float* aabbf = reinterpret_cast<float*>(ordf + 6 * n_components);  // GENERIC: node boxes of the interpreter
   {
     const BlobHeader* h = reinterpret_cast<const BlobHeader*>(s_mem);
     const OrderEntry* ord = reinterpret_cast<const OrderEntry*>(s_mem + h->off_order);
     for (int e = threadIdx.x; e < 6 * h->n_boxed; e += blockDim.x) convert_order(ord[e], ordf[e]);
+    if (GENERIC) {
+      const double* box = reinterpret_cast<const double*>(s_mem + h->off_aabb);
+      for (int e = threadIdx.x; e < 6 * h->n_aabb; e += blockDim.x)
+        aabbf[e] = (e % 6 & 1) ? to_float_up(box[e]) : to_float_dn(box[e]);
+    }
     const Leaf* leaves = reinterpret_cast<const Leaf*>(s_mem + h->off_leaves);
     const Comp* comps = reinterpret_cast<const Comp*>(s_mem + h->off_comps);
     for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) convert_leaf(leaves[l], lf[l]);
@@ -79,6 +97,11 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
   // variant, which carries none of the table walk)
   sc.order = ORDERED ? ordf : nullptr;
   sc.unboxed = reinterpret_cast<const int*>(s_mem + sc.h->off_unboxed);
+  sc.ops = reinterpret_cast<const Op*>(s_mem + sc.h->off_ops);
+  sc.aabb = GENERIC ? aabbf : nullptr;
+  // hit lists of the interpreter (local memory): only the GENERIC variants carry them
+  typename StackForF<GENERIC>::type stack_storage;
+  HitStackF* S = StackForF<GENERIC>::ptr(stack_storage);
 
   const long long tile = blockIdx.x;
   const long long i = tile * kTileRays + threadIdx.x;
@@ -115,7 +138,7 @@ __global__ void __launch_bounds__(kTileRays, PRT_F32_MIN_BLOCKS) trace_kernel_f3
       vn = step_speed(rs, ctr);
       if (vn != 0.0f) {
         bool tie = false;
-        nearest_hit<ORDERED>(sc, rs, ray_scale(rs), hit_t, hit_leaf, tie);
+        nearest_hit<ORDERED, GENERIC>(sc, rs, ray_scale(rs), S, hit_t, hit_leaf, tie);
         if (tie) ctr.w1 |= kCtrTie;
       }
     }
@@ -259,25 +282,33 @@ __global__ void __launch_bounds__(kTileRays) gather_kernel_f32(const GatherArgs 
 extern "C" {
 
 // dynamic shared memory of trace_kernel_f32 for a scene
-size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components) {
+size_t prt_f32_smem_bytes(int blob_bytes, int n_leaves, int n_components, int n_aabb) {
   return (size_t)prt::f32::blob_aligned(blob_bytes) + (size_t)n_leaves * sizeof(prt::f32::LeafF) +
-         (size_t)n_components * sizeof(prt::f32::CompF) + (size_t)6 * n_components * sizeof(prt::f32::OrderEntryF);
+         (size_t)n_components * sizeof(prt::f32::CompF) + (size_t)6 * n_components * sizeof(prt::f32::OrderEntryF) +
+         (size_t)6 * n_aabb * sizeof(float);
 }
 
-// ordered != 0: the scene's header asks for the ray-ordered walk (BlobHeader.flags bits 2 and 3, n_boxed > 0)
-cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int ordered, int n_leaves, int n_components,
-                                 cudaStream_t st) {
+// ordered != 0: the scene's header asks for the ray-ordered walk (BlobHeader.flags bits 2 and 3, n_boxed > 0);
+// generic != 0: some component needs the interpreter for arbitrary CSG trees (n_aabb = its node boxes)
+cudaError_t prt_launch_trace_f32(const prt::TraceArgs* a, int record, int ordered, int generic, int n_leaves,
+                                 int n_components, int n_aabb, cudaStream_t st) {
   const long long tiles = (a->n_rays + prt::kTileRays - 1) / prt::kTileRays;
   if (tiles == 0) return cudaSuccess;
-  const size_t smem = prt_f32_smem_bytes(a->blob_bytes, n_leaves, n_components);
+  const size_t smem = prt_f32_smem_bytes(a->blob_bytes, n_leaves, n_components, generic ? n_aabb : 0);
   auto launch = [&](auto kernel) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<(unsigned)tiles, prt::kTileRays, smem, st>>>(*a, n_leaves, n_components);
   };
-  if (ordered) {
-    if (record) launch(prt::f32::trace_kernel_f32<true, true>); else launch(prt::f32::trace_kernel_f32<false, true>);
-  } else {
-    if (record) launch(prt::f32::trace_kernel_f32<true, false>); else launch(prt::f32::trace_kernel_f32<false, false>);
+  const int variant = (record ? 4 : 0) | (ordered ? 2 : 0) | (generic ? 1 : 0);
+  switch (variant) {
+    case 0: launch(prt::f32::trace_kernel_f32<false, false, false>); break;
+    case 1: launch(prt::f32::trace_kernel_f32<false, false, true>); break;
+    case 2: launch(prt::f32::trace_kernel_f32<false, true, false>); break;
+    case 3: launch(prt::f32::trace_kernel_f32<false, true, true>); break;
+    case 4: launch(prt::f32::trace_kernel_f32<true, false, false>); break;
+    case 5: launch(prt::f32::trace_kernel_f32<true, false, true>); break;
+    case 6: launch(prt::f32::trace_kernel_f32<true, true, false>); break;
+    default: launch(prt::f32::trace_kernel_f32<true, true, true>); break;
   }
   return cudaGetLastError();
 }

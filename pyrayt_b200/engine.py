@@ -104,7 +104,7 @@ class Engine:
 
         precision: "fp64" (the reference's arithmetic, bit-exact against the oracle) or "fp32", the optional fast
         mode (PRT_FLAG_FP32, include/pyrayt_b200.h): the generation loop in single precision, frame values
-        within 1e-5 of the scene scale of the FP64 frame; scenes of bare surfaces and left-deep CSG trees only.
+        within 1e-5 of the scene scale of the FP64 frame; scenes that fit shared memory.
 
         diagnose: PRT_FLAG_DIAGNOSE -- also count the rays "within 1e-9 of grazing or CSG seams" (counters
         ``grazing_rays`` / ``seam_rays``: the nearest-hit answer of some generation changes when the origin is

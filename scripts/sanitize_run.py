@@ -51,10 +51,9 @@ for name in GOLDEN_CASES:
     diag = eng.trace(d, generation_limit=gl, diagnose=True)  # PRT_FLAG_DIAGNOSE variant
     odiag = oracle.diagnose(scene, rays, gl)
     assert (diag.counters["grazing_rays"], diag.counters["seam_rays"]) == (odiag["grazing_rays"], odiag["seam_rays"]), name
-    if name != "nested_csg":  # the FP32 fast mode: trace + ordering + host transfer
-        f32 = eng.trace(d, generation_limit=gl, precision="fp32", to_host=True)
-        assert abs(f32.rows - want.shape[1]) <= max(2, want.shape[1] // 100), name
-        eng.trace(d, generation_limit=gl, precision="fp32", record="none")
+    f32 = eng.trace(d, generation_limit=gl, precision="fp32", to_host=True)  # the FP32 fast mode: trace + ordering + host transfer
+    assert abs(f32.rows - want.shape[1]) <= max(2, want.shape[1] // 100), name
+    eng.trace(d, generation_limit=gl, precision="fp32", record="none")
     full = eng.trace(d, generation_limit=gl)
     if full.rows:
         analytics.spot_stats(full, max(1, rays.shape[1] // 3), 3, surface=sid)

@@ -64,8 +64,6 @@ def trace_f32(scene, rays, generation_limit, ray_offset=1e-6):
                                  ctypes.c_longlong(n), ctypes.c_int(generation_limit), ctypes.c_double(ray_offset),
                                  rows.ctypes.data_as(_dp), ctypes.c_longlong(cap),
                                  nrows.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
-    if total == -5:
-        return None
     assert total >= 0
     rows = rows[:total]
     rnd = np.concatenate([np.arange(k) for k in nrows[:n]]) if total else np.zeros(0, dtype=np.int64)

@@ -107,8 +107,7 @@ long long prt_emul_trace(const prt_scene_desc* d, const double* rays, long long 
 
 // The FP32 fast mode's per-ray code (prt_device_f32.cuh) on the host: same driver loop as trace_kernel_f32,
 // rows expanded as gather_kernel_f32 does.  (The host compiler does not contract to FMA, so values differ
-// from the device in the last bits; the mode's contract is a tolerance.)  Returns rows, -1 bad scene,
-// -5 when the scene needs the generic interpreter (unsupported in this mode).
+// from the device in the last bits; the mode's contract is a tolerance.)  Returns rows, -1 bad scene.
 long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long long n, long long stride,
                              int generation_limit, double ray_offset, double* rows_out, long long cap, int* nrows) {
   std::vector<unsigned char> blob;
@@ -116,7 +115,6 @@ long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long l
   std::string err;
   if (prt::encode_scene(d, blob, slots, err) != PRT_OK) return -1;
   const prt::SceneView sv = prt::make_view(blob.data());
-  if (sv.h->flags & 2) return -5;
   std::vector<prt::f32::LeafF> lf(sv.h->n_leaves);
   std::vector<prt::f32::CompF> cf(sv.h->n_components);
   for (int l = 0; l < sv.h->n_leaves; ++l) prt::f32::convert_leaf(sv.leaves[l], lf[l]);
@@ -126,8 +124,12 @@ long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long l
   // PRT_EMUL_F32_LIST / PRT_EMUL_F32_ORDERED force one of the two walks (the kernel follows the encoder: flags bit 3)
   const bool walk = sv.h->n_boxed > 0 && (sv.h->flags & 4) && !std::getenv("PRT_EMUL_F32_LIST") &&
                     ((sv.h->flags & 8) || std::getenv("PRT_EMUL_F32_ORDERED"));
+  std::vector<float> aabbf(6 * (size_t)sv.h->n_aabb + 1);
+  for (int e = 0; e < 6 * sv.h->n_aabb; ++e)
+    aabbf[e] = (e % 6 & 1) ? prt::f32::to_float_up(sv.aabb[e]) : prt::f32::to_float_dn(sv.aabb[e]);
   prt::f32::SceneViewF sc = {sv.h, sv.comps, sv.leaves, lf.data(), cf.data(), walk ? ordf.data() : nullptr,
-                             sv.unboxed};
+                             sv.unboxed, sv.ops, aabbf.data()};
+  prt::f32::HitStackF S;
   long long total = 0;
   for (long long i = 0; i < n; ++i) {
     prt::f32::RayStateF r = {(float)rays[0 * stride + i], (float)rays[1 * stride + i], (float)rays[2 * stride + i],
@@ -143,8 +145,8 @@ long long prt_emul_trace_f32(const prt_scene_desc* d, const double* rays, long l
       float t;
       int leaf;
       bool tie = false;
-      if (walk) prt::f32::nearest_hit<true>(sc, r, prt::f32::ray_scale(r), t, leaf, tie);
-      else prt::f32::nearest_hit<false>(sc, r, prt::f32::ray_scale(r), t, leaf, tie);
+      if (walk) prt::f32::nearest_hit<true, true>(sc, r, prt::f32::ray_scale(r), &S, t, leaf, tie);
+      else prt::f32::nearest_hit<false, true>(sc, r, prt::f32::ray_scale(r), &S, t, leaf, tie);
       if (leaf < 0) break;
       if (lf[leaf].mat == PRT_MAT_UNTRACEABLE) break;
       if (total < cap) {
