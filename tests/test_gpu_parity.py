@@ -118,6 +118,13 @@ def test_fp32_fast_mode_limits(cuda_device):
     assert none.counters["segments"] == full.rows and none.counters["generations"] == full.counters["generations"]
     empty = eng.trace(d[:, :0], generation_limit=gl, precision="fp32")
     assert empty.rows == 0
+    # record only the rows that end on one surface; staging overflow and the exact retry
+    sid = int(scene.leaf_sid[-1])
+    only = eng.trace(d, generation_limit=gl, precision="fp32", record="surface", detector_sid=sid)
+    f = full.frame
+    assert torch.equal(only.frame, f[:, f[5] == float(sid)])
+    small = eng.trace(d, generation_limit=gl, precision="fp32", capacity=64)
+    assert torch.equal(small.frame, f)
 
 
 def test_edge_inputs(cuda_device):
