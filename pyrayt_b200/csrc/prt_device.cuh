@@ -87,10 +87,12 @@ PRT_HD bool mags_in_window(unsigned mn, unsigned mx) {
   return (mn >= (kExpLo << 20)) & (mx < ((kExpLo + kExpSpan) << 20));
 }
 
-PRT_HD Rcp make_rcp(double b) {
+
+// the reciprocal alone: the caller tests the denominator's window together with its numerators (mags_in_window)
+PRT_HD Rcp make_rcp_unchecked(double b) {
   Rcp R;
   R.b = b;
-  R.lim = (exp_of(b) - kExpLo < kExpSpan) ? kExpSpan : 0u;  // |b| in [2^-900, 2^900), finite
+  R.lim = kExpSpan;
 #if defined(__CUDA_ARCH__)
   R.r = __drcp_rn(b);
 #else
@@ -98,6 +100,7 @@ PRT_HD Rcp make_rcp(double b) {
 #endif
   return R;
 }
+PRT_HD unsigned lim_of(double b) { return (exp_of(b) - kExpLo < kExpSpan) ? kExpSpan : 0u; }
 
 // RN(a / R.b) without guards; exact when a is 0 or has |a| in [2^-900, 2^900) and R.lim != 0
 PRT_HD double div_fast(double a, const Rcp& R) {
@@ -118,7 +121,7 @@ PRT_HD double div_by(double a, const Rcp& R) {
   return slow_div(a, R.b);  // tiny, huge, inf, NaN or an unsafe denominator: one shared IEEE division
 }
 
-// Two / three quotients by the same denominator: the 3-instruction form is computed for all of them
+// Two quotients by a prepared reciprocal (a slab of the rare generic box test): the 3-instruction form is computed for both
 // and one test decides whether any needs the guarded path (one branch instead of one per quotient).
 PRT_HD void div_by2(double a0, double a1, const Rcp& R, double& q0, double& q1) {
   q0 = div_fast(a0, R);
@@ -130,13 +133,31 @@ PRT_HD void div_by2(double a0, double a1, const Rcp& R, double& q0, double& q1) 
     q1 = div_by(a1, R);
   }
 }
-PRT_HD void div_by3(double a0, double a1, double a2, const Rcp& R, double& q0, double& q1, double& q2) {
+
+// a0/b, a1/b: one window test for the denominator and the two numerators together
+PRT_HD void div2_by_value(double a0, double a1, double b, double& q0, double& q1) {
+  Rcp R = make_rcp_unchecked(b);
+  q0 = div_fast(a0, R);
+  q1 = div_fast(a1, R);
+  const unsigned m0 = mag_of(a0), m1 = mag_of(a1), mb = mag_of(b);
+  const bool ok = mags_in_window(umin2(umin2(m0, m1), mb), umax2(umax2(m0, m1), mb));
+  if (!ok) {
+    R.lim = lim_of(b);
+    q0 = div_by(a0, R);
+    q1 = div_by(a1, R);
+  }
+}
+
+// a0/b, a1/b, a2/b: one window test for the denominator and the three numerators together
+PRT_HD void div3_by_value(double a0, double a1, double a2, double b, double& q0, double& q1, double& q2) {
+  Rcp R = make_rcp_unchecked(b);
   q0 = div_fast(a0, R);
   q1 = div_fast(a1, R);
   q2 = div_fast(a2, R);
-  const unsigned m0 = mag_of(a0), m1 = mag_of(a1), m2 = mag_of(a2);
-  const bool ok = (R.lim != 0u) & mags_in_window(umin2(umin2(m0, m1), m2), umax2(umax2(m0, m1), m2));
+  const unsigned m0 = mag_of(a0), m1 = mag_of(a1), m2 = mag_of(a2), mb = mag_of(b);
+  const bool ok = mags_in_window(umin2(umin2(m0, m1), umin2(m2, mb)), umax2(umax2(m0, m1), umax2(m2, mb)));
   if (!ok) {
+    R.lim = lim_of(b);
     q0 = div_by(a0, R);
     q1 = div_by(a1, R);
     q2 = div_by(a2, R);
@@ -147,8 +168,7 @@ PRT_HD void div_by3(double a0, double a1, double a2, const Rcp& R, double& q0, d
 struct RayInv {
   double r0, r1, r2;  // RN(1 / (d_k + z_k))
   unsigned bits;      // 0-2: z_k (|d_k| <= 1e-8), 3-5: s_k (1 if the ray runs towards -axis: near face = hi),
-                      // 6: fast (guard-free slab arithmetic is provably exact for this ray, see cube_hits),
-                      // 7-9: reciprocal k usable by div_by (denominator in the safe exponent window)
+                      // 6: fast (guard-free slab arithmetic is provably exact for this ray, see cube_hits)
 };
 
 struct SceneView {
@@ -181,9 +201,9 @@ PRT_HD SceneView make_view(const unsigned char* blob) {
 PRT_HD void clip_z(double s0, double s1, double zlo, double zhi, double oz, double dz,
                                        double b0_num, double& t0, double& t1) {
   const bool par = isz(dz);
-  const Rcp den = make_rcp(dz + (par ? 1.0 : 0.0));
+  const double den_b = dz + (par ? 1.0 : 0.0);
   double b0, b1;
-  div_by2(b0_num, zhi - oz, den, b0, b1);
+  div2_by_value(b0_num, zhi - oz, den_b, b0, b1);
   if (par) {
     b0 = ((oz >= zlo) && (oz <= zhi)) ? -PRT_INF : PRT_INF;
     b1 = PRT_INF;
@@ -223,7 +243,7 @@ PRT_HD RayInv make_ray_inv(double o0, double o1, double o2, double d0, double d1
   RayInv I;
   const bool z0 = isz(d0), z1 = isz(d1), z2 = isz(d2);
   const double e0 = d0 + (z0 ? 1.0 : 0.0), e1 = d1 + (z1 ? 1.0 : 0.0), e2 = d2 + (z2 ? 1.0 : 0.0);
-  const Rcp R0 = make_rcp(e0), R1 = make_rcp(e1), R2 = make_rcp(e2);
+  const Rcp R0 = make_rcp_unchecked(e0), R1 = make_rcp_unchecked(e1), R2 = make_rcp_unchecked(e2);
   I.r0 = R0.r;
   I.r1 = R1.r;
   I.r2 = R2.r;
@@ -232,8 +252,7 @@ PRT_HD RayInv make_ray_inv(double o0, double o1, double o2, double d0, double d1
   const bool den_ok = (exp_of(e0) - 957u < 132u) & (exp_of(e1) - 957u < 132u) & (exp_of(e2) - 957u < 132u);
   const bool fast = boxes_tame & !z0 & !z1 & !z2 & den_ok & tame(o0) & tame(o1) & tame(o2);
   I.bits = (z0 ? 1u : 0u) | (z1 ? 2u : 0u) | (z2 ? 4u : 0u) | (e0 < 0 ? 8u : 0u) | (e1 < 0 ? 16u : 0u) |
-           (e2 < 0 ? 32u : 0u) | (fast ? 64u : 0u) | (R0.lim ? 128u : 0u) | (R1.lim ? 256u : 0u) |
-           (R2.lim ? 512u : 0u);
+           (e2 < 0 ? 32u : 0u) | (fast ? 64u : 0u);
   return I;
 }
 
@@ -241,9 +260,11 @@ PRT_HD RayInv make_ray_inv(double o0, double o1, double o2, double d0, double d1
 PRT_HD void cube_hits_generic(const double* sp, double o0, double o1, double o2, double d0, double d1, double d2,
                                    const RayInv& I, double& lo, double& hi) {
   const bool z0 = I.bits & 1u, z1 = I.bits & 2u, z2 = I.bits & 4u;
-  const Rcp R0 = {d0 + (z0 ? 1.0 : 0.0), I.r0, (I.bits & 128u) ? kExpSpan : 0u};
-  const Rcp R1 = {d1 + (z1 ? 1.0 : 0.0), I.r1, (I.bits & 256u) ? kExpSpan : 0u};
-  const Rcp R2 = {d2 + (z2 ? 1.0 : 0.0), I.r2, (I.bits & 512u) ? kExpSpan : 0u};
+  // (rare path: the windows of the three denominators are tested here, not once per generation)
+  const double e0 = d0 + (z0 ? 1.0 : 0.0), e1 = d1 + (z1 ? 1.0 : 0.0), e2 = d2 + (z2 ? 1.0 : 0.0);
+  const Rcp R0 = {e0, I.r0, lim_of(e0)};
+  const Rcp R1 = {e1, I.r1, lim_of(e1)};
+  const Rcp R2 = {e2, I.r2, lim_of(e2)};
   double mn0, mx0, mn1, mx1, mn2, mx2;
   cube_axis(o0, z0, R0, sp[0], sp[1], mn0, mx0);
   cube_axis(o1, z1, R1, sp[2], sp[3], mn1, mx1);
@@ -285,9 +306,9 @@ PRT_HD void cube_hits(const double* sp, double o0, double o1, double o2, double 
 PRT_HD void plane_axis(double o, double d, double dim, double& mn, double& mx) {
   const bool zf = isz(d);
   const double half = dim / 2;
-  const Rcp den = make_rcp(d + (zf ? 1.0 : 0.0));
+  const double den_b = d + (zf ? 1.0 : 0.0);
   double v0, v1;
-  div_by2(-(o - half), -(o + half), den, v0, v1);
+  div2_by_value(-(o - half), -(o + half), den_b, v0, v1);
   if (zf) {
     v0 = (fabs(o) <= half) ? -PRT_INF : PRT_INF;
     v1 = PRT_INF;
@@ -315,8 +336,8 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double c = (o0 * o0 + o1 * o1 + o2 * o2) - r * r;
       const double disc = b * b - 4 * a * c;
       const double root = sqrt(fmax(0.0, disc));
-      const Rcp den = make_rcp(2 * a);
-      div_by2(-b + root, -b - root, den, t0, t1);
+      const double den_b = 2 * a;
+      div2_by_value(-b + root, -b - root, den_b, t0, t1);
       if (!(disc >= 0)) {
         t0 = PRT_INF;
         t1 = PRT_INF;
@@ -331,9 +352,9 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double disc = b * b - 4 * a * c;
       const bool lin = isz(a);
       const double root = sqrt(fmax(0.0, disc));
-      const Rcp den = make_rcp(2 * a + (lin ? 1.0 : 0.0));
+      const double den_b = 2 * a + (lin ? 1.0 : 0.0);
       double s0, s1;
-      div_by2(-b + root, -b - root, den, s0, s1);
+      div2_by_value(-b + root, -b - root, den_b, s0, s1);
       if (!(disc >= 0)) {
         s0 = PRT_INF;
         s1 = PRT_INF;
@@ -358,9 +379,9 @@ PRT_HD void leaf_hits(const Leaf& L, double p0, double p1, double p2, double v0,
       const double disc = b * b - 4 * a * c;
       const bool lin = isz(a);
       const double root = sqrt(fmax(0.0, disc));
-      const Rcp den = make_rcp(2 * a + (lin ? 1.0 : 0.0));
+      const double den_b = 2 * a + (lin ? 1.0 : 0.0);
       double s0, s1;
-      div_by2(-b + root, -b - root, den, s0, s1);
+      div2_by_value(-b + root, -b - root, den_b, s0, s1);
       if (!(disc >= 0)) {
         s0 = PRT_INF;
         s1 = PRT_INF;
@@ -425,10 +446,8 @@ PRT_HD void sphere_pair_hits(const Leaf& A, const Leaf& B, double p0, double p1,
   const double bdisc = bb * bb - 4 * ba * bc;
   const double aroot = sqrt(fmax(0.0, adisc));
   const double broot = sqrt(fmax(0.0, bdisc));
-  const Rcp aden = make_rcp(2 * aa);
-  const Rcp bden = make_rcp(2 * ba);
-  div_by2(-ab + aroot, -ab - aroot, aden, a0, a1);
-  div_by2(-bb + broot, -bb - broot, bden, b0, b1);
+  div2_by_value(-ab + aroot, -ab - aroot, 2 * aa, a0, a1);
+  div2_by_value(-bb + broot, -bb - broot, 2 * ba, b0, b1);
   if (!(adisc >= 0)) {
     a0 = PRT_INF;
     a1 = PRT_INF;
@@ -490,10 +509,11 @@ PRT_HD bool lens3_hits_fast(const Leaf& Y, const Leaf& A, const Leaf& B, double 
   const double broot = sqrt(fmax(0.0, bdisc));
   // the literal code's rare branches: isclose(a, 0) in binomial_root, isclose(d_z, 0) in the cap clip
   const bool rare = isz(ya) | isz(yd2);
-  const Rcp yden = make_rcp(2 * ya + 0.0);
-  const Rcp aden = make_rcp(2 * aa);
-  const Rcp bden = make_rcp(2 * ba);
-  const Rcp zden = make_rcp(yd2 + 0.0);
+  const double yd = 2 * ya + 0.0, ad = 2 * aa, bd = 2 * ba, zd = yd2 + 0.0;
+  const Rcp yden = make_rcp_unchecked(yd);
+  const Rcp aden = make_rcp_unchecked(ad);
+  const Rcp bden = make_rcp_unchecked(bd);
+  const Rcp zden = make_rcp_unchecked(zd);
   const double yn0 = -yb + yroot, yn1 = -yb - yroot;
   const double an0 = -ab + aroot, an1 = -ab - aroot;
   const double bn0 = -bb + broot, bn1 = -bb - broot;
@@ -506,9 +526,12 @@ PRT_HD bool lens3_hits_fast(const Leaf& Y, const Leaf& A, const Leaf& B, double 
   double c0 = div_fast(zn0, zden), c1 = div_fast(zn1, zden);
   const unsigned my0 = mag_of(yn0), my1 = mag_of(yn1), ma0 = mag_of(an0), ma1 = mag_of(an1);
   const unsigned mb0 = mag_of(bn0), mb1 = mag_of(bn1), mz0 = mag_of(zn0), mz1 = mag_of(zn1);
-  const unsigned mn = umin2(umin2(umin2(my0, my1), umin2(ma0, ma1)), umin2(umin2(mb0, mb1), umin2(mz0, mz1)));
-  const unsigned mx = umax2(umax2(umax2(my0, my1), umax2(ma0, ma1)), umax2(umax2(mb0, mb1), umax2(mz0, mz1)));
-  const bool ok = ((yden.lim != 0u) & (aden.lim != 0u) & (bden.lim != 0u) & (zden.lim != 0u)) & mags_in_window(mn, mx);
+  const unsigned dy = mag_of(yd), da = mag_of(ad), db = mag_of(bd), dz = mag_of(zd);  // the four denominators
+  const unsigned mn = umin2(umin2(umin2(umin2(my0, my1), umin2(ma0, ma1)), umin2(umin2(mb0, mb1), umin2(mz0, mz1))),
+                            umin2(umin2(dy, da), umin2(db, dz)));
+  const unsigned mx = umax2(umax2(umax2(umax2(my0, my1), umax2(ma0, ma1)), umax2(umax2(mb0, mb1), umax2(mz0, mz1))),
+                            umax2(umax2(dy, da), umax2(db, dz)));
+  const bool ok = mags_in_window(mn, mx);
   if (!(ydisc >= 0)) {
     s0 = PRT_INF;
     s1 = PRT_INF;
@@ -594,15 +617,13 @@ PRT_HD void world_normal(const Leaf& L, double p0, double p1, double p2, double&
       break;
   }
   if (!unit) {
-    const Rcp nrm = make_rcp(sqrt(a0 * a0 + a1 * a1 + a2 * a2));
-    div_by3(a0, a1, a2, nrm, a0, a1, a2);
+    div3_by_value(a0, a1, a2, sqrt(a0 * a0 + a1 * a1 + a2 * a2), a0, a1, a2);
   }
   // M_obj^T n_obj, w dropped, normalise, flip (world_objects.py:411-418)
   double w0 = L.m[0] * a0 + L.m[4] * a1 + L.m[8] * a2;
   double w1 = L.m[1] * a0 + L.m[5] * a1 + L.m[9] * a2;
   double w2 = L.m[2] * a0 + L.m[6] * a1 + L.m[10] * a2;
-  const Rcp wn = make_rcp(sqrt(w0 * w0 + w1 * w1 + w2 * w2));
-  div_by3(w0, w1, w2, wn, n0, n1, n2);
+  div3_by_value(w0, w1, w2, sqrt(w0 * w0 + w1 * w1 + w2 * w2), n0, n1, n2);
   n0 *= L.nscale;
   n1 *= L.nscale;
   n2 *= L.nscale;
@@ -1090,8 +1111,7 @@ PRT_HD double step_speed(const RayState& r, StepCounters& c) {
 // One definition, used by the interaction (refract()'s normalised vector is the same quotient,
 // operations.py:125) and by the ordering pass that rebuilds the columns from the staged direction.
 PRT_HD void unit_tilt(double v0, double v1, double v2, double vn, double& t0, double& t1, double& t2) {
-  const Rcp rvn = make_rcp(vn);
-  div_by3(v0, v1, v2, rvn, t0, t1, t2);
+  div3_by_value(v0, v1, v2, vn, t0, t1, t2);
 }
 
 // second half: _st_interact for a ray whose nearest hit is (best_t, best_leaf >= 0); `vn` = step_speed.
@@ -1161,8 +1181,7 @@ PRT_HD bool step_interact(const SceneView& sc, const RayState& r, int g, int gen
       o.nv1 = u1 + k * n1;
       o.nv2 = u2 + k * n2;
     }
-    const Rcp nn = make_rcp(sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2));
-    div_by3(o.nv0, o.nv1, o.nv2, nn, o.nv0, o.nv1, o.nv2);
+    div3_by_value(o.nv0, o.nv1, o.nv2, sqrt(o.nv0 * o.nv0 + o.nv1 * o.nv1 + o.nv2 * o.nv2), o.nv0, o.nv1, o.nv2);
     // when exiting, n0..n2 were flipped above and now hold minus the outward normal: a refracted ray
     // has a positive outward component, a totally reflected one a negative one
     o.skip = leaves_for_good(sc, L, exiting ? -(o.nv0 * n0 + o.nv1 * n1 + o.nv2 * n2) : -1.0);
