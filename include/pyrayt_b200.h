@@ -154,7 +154,9 @@ typedef struct prt_params {
  * and the refractive index), surface and generation ids agree except for rays passing within that distance
  * of an edge or seam.  A ray cannot leave a surface by the reference's 1e-6 offset in single precision
  * (ulp(100) = 7.6e-6): instead, roots of the leaf just hit that lie within 2e-4 x max(1, |origin|) of the
- * origin are taken as the crossing just made.  Every scene the FP64 path stages in shared memory is accepted
+ * origin are taken as the crossing just made (so features of the scene -- thicknesses, gaps between surfaces
+ * of one leaf -- must be well above 2e-4 length units, as they must be well above the reference's own 1e-6
+ * offset in FP64).  Every scene the FP64 path stages in shared memory is accepted
  * (arbitrary CSG trees run a single-precision interpreter); scenes too large for that return PRT_ERR_LIMIT.
  * Staged records are 40 bytes (5 of the PRT_STAGE_COLS columns): pass PRT_LAYOUT_FP32_RECORDS in
  * prt_gather_frame's layout.
